@@ -1,0 +1,175 @@
+/*
+ * lbm_b200.h -- C ABI of the B200-native D2Q9 time step (liblbm_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of jviquerat/lbm.  The reference
+ * has no FFI of its own: its seam is the `lattice` class, whose compute methods
+ * each forward to one Numba kernel (lbm/src/core/lattice.py:178-286 ->
+ * lbm/src/core/nb.py).  Every entry point below names the reference interface it
+ * replaces.  lbm_b200/lattice.py binds these with ctypes and presents the
+ * reference's `lattice` surface; INTEGRATION.md shows the binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no C++/torch types cross the boundary;
+ *   - every call returns LBM_OK (0) or a negative error code and never throws;
+ *     lbm_last_error() returns a message for the last failure on this thread;
+ *   - the library never takes ownership of caller memory; device buffers bound
+ *     with lbm_bind_state stay owned by the caller (a torch tensor);
+ *   - all device work is enqueued on the stream given to lbm_set_stream (default:
+ *     the CUDA legacy stream); only the lbm_get_* calls and lbm_sync wait for it;
+ *   - one host thread per handle.
+ *
+ * Field layout on the HOST side is the reference's: C-ordered [q][i][j] with
+ * i = x (0..nx-1), j = y (0..ny-1), j contiguous (lattice.py:155-174); element
+ * type = the handle's dtype.  D2Q9 numbering, weights and opposite table are
+ * lattice.py:135-152.
+ *
+ * Time-step formulation.  The state carried between steps is
+ * the post-collision population array F (= the reference's g_up).  One lbm_step
+ * "update" executes, fused in one kernel,
+ *     stream (pull)  ->  obstacle (I)BB  ->  Zou-He walls + corners   [of reference iteration it-1]
+ *     -> macro -> equilibrium -> TRT collision                        [of reference iteration it]
+ * which is exactly run.py:33-45 regrouped.  The very first update after
+ * lbm_set_populations / lbm_init_equilibrium is collide-only (iteration 0).
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_ABI_VERSION 1
+
+/* error codes */
+#define LBM_OK            0
+#define LBM_E_INVALID    -1  /* bad argument */
+#define LBM_E_CUDA       -2  /* CUDA runtime error (message has the detail) */
+#define LBM_E_STATE      -3  /* call not valid in the handle's current state */
+#define LBM_E_NOMEM      -4
+#define LBM_E_UNSUPPORTED -5
+
+/* lbm_cfg.dtype */
+#define LBM_F64 0
+#define LBM_F32 1
+/* lbm_cfg.arith: LBM_ARITH_FUSED lets the compiler contract a*b+c into FMAs (production);
+ * LBM_ARITH_STRICT evaluates every expression with separately rounded IEEE operations in the
+ * order the reference writes them -- bit-identical to oracle/lbm_oracle.c (parity tests). */
+#define LBM_ARITH_FUSED  0
+#define LBM_ARITH_STRICT 1
+/* lbm_cfg.right_wall: which Zou-He variant closes the right side
+ * (nb_zou_he_right_wall_velocity nb.py:147-169 / nb_zou_he_right_wall_pressure nb.py:173-195). */
+#define LBM_RIGHT_VELOCITY 0
+#define LBM_RIGHT_PRESSURE 1
+
+/* lbm_step flags */
+#define LBM_STEP_MACRO_LAST 1u /* the last update of the call also stores rho,u (lattice.macro) */
+
+/* lbm_get_populations `which` */
+#define LBM_POP_POST_COLLISION 0 /* F  == reference g_up */
+#define LBM_POP_STREAMED       1 /* g  == reference g (valid after set_populations or lbm_apply_bc) */
+
+typedef struct lbm_handle lbm_t;
+
+typedef struct lbm_cfg {
+    int64_t nx, ny;    /* global lattice size (lattice.nx, lattice.ny) */
+    int64_t x0, nxl;   /* x-slab owned by this handle: global columns [x0, x0+nxl); one GPU: 0, nx */
+    double  om_p, om_m;/* TRT rates lattice.om_p_lbm / om_m_lbm (lattice.py:127-131) */
+    int32_t dtype;     /* LBM_F64 | LBM_F32 */
+    int32_t arith;     /* LBM_ARITH_FUSED | LBM_ARITH_STRICT */
+    int32_t right_wall;/* LBM_RIGHT_VELOCITY | LBM_RIGHT_PRESSURE */
+    int32_t device;    /* CUDA device ordinal */
+} lbm_cfg;
+
+/* Memory layout of one population buffer, for callers that allocate it themselves (torch) and
+ * for the slab halo exchange: element (q, x, y), x in [-1, nxl] (x = -1 and x = nxl are the halo
+ * columns), lives at element offset  origin + q*plane + x*pitch + y. */
+typedef struct lbm_layout {
+    int64_t elems;  /* elements in one buffer */
+    int64_t origin; /* offset of (q=0, x=0, y=0) */
+    int64_t plane;  /* elements between consecutive q */
+    int64_t pitch;  /* elements between consecutive x */
+    int64_t elem_size;
+} lbm_layout;
+
+int lbm_abi_version(void);
+const char *lbm_last_error(void);
+
+/* Replaces lattice.__init__/set_default_lbm array allocation (lattice.py:117-174). */
+int lbm_create(const lbm_cfg *cfg, lbm_t **out);
+int lbm_destroy(lbm_t *h);
+int lbm_get_layout(const lbm_t *h, lbm_layout *out);
+/* Bind two caller-owned device buffers of layout.elems elements each (they are zero-filled).
+ * Optional: without it the library allocates its own on first use. */
+int lbm_bind_state(lbm_t *h, void *dev_a, void *dev_b, size_t bytes_each);
+/* Device address of the buffer that holds the current / the other population array. */
+int lbm_state_ptrs(const lbm_t *h, void **current, void **other);
+int lbm_set_stream(lbm_t *h, void *cuda_stream);
+int lbm_sync(lbm_t *h);
+/* Switch the right-side Zou-He variant for the following updates (the apps choose it by which
+ * lattice.zou_he_right_wall_* method their set_bc calls: cavity.py:84 vs turek.py:121). */
+int lbm_set_right_wall(lbm_t *h, int32_t right_wall);
+
+/* lattice.g = ... (cavity.py:62, turek.py:91): upload pre-collision populations g[9][nxl][ny]. */
+int lbm_set_populations(lbm_t *h, const void *g_host);
+/* Same state without a host array: g_q = equilibrium(rho, ux, uy) everywhere, computed on the
+ * device (what the apps' initialize() produces with u = 0: cavity.py:54-62). */
+int lbm_init_equilibrium(lbm_t *h, double rho, double ux, double uy);
+/* nb_equilibrium (nb.py:7-17) on host fields rho[nxl][ny], u[2][nxl][ny] -> g_eq[9][nxl][ny]. */
+int lbm_equilibrium(lbm_t *h, const void *rho_host, const void *u_host, void *g_eq_host);
+
+/* Obstacle link lists, replaces the per-obstacle arguments of nb_bounce_back_obstacle
+ * (nb.py:77-117) and nb_drag_lift (nb.py:49-73).  Obstacle o owns links
+ * offsets[o] .. offsets[o+1]-1; ijq holds rows (i, j, q) with GLOBAL i, q pointing from the fluid
+ * node into the solid (lattice.py:336-341); ibb[k] is the wall distance (ignored if !use_ibb).
+ * Links outside this handle's slab are dropped.  Negative or out-of-range indices (the
+ * reference wraps them silently) are rejected with LBM_E_INVALID. */
+int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const int64_t *ijq,
+                  const double *ibb, int32_t use_ibb);
+
+/* Wall profiles, replaces the u_left/u_right/u_top/u_bot/rho_right arguments of the nb_zou_he_*
+ * kernels (lattice.py:160-164).  One row = [u_left(2*ny) | u_right(2*ny) | u_top(2*nx) |
+ * u_bot(2*nx) | rho_right(ny)] doubles, component-major as in the reference, GLOBAL sizes.
+ * Copies n_rows rows into the device table (replacing it).  If rows_host is pinned memory the
+ * copy is asynchronous: keep it unchanged until the next lbm_sync / lbm_get_*. */
+int64_t lbm_wall_row_len(const lbm_t *h);
+int lbm_set_walls(lbm_t *h, int64_t n_rows, const double *rows_host);
+
+/* n_updates fused updates; update s uses wall row first_row + s*row_stride and stores the
+ * momentum-exchange sums of every obstacle in force slot s.  Replaces one pass of
+ * run.py:33-45 (macro, equilibrium, collision_stream, set_bc) per update. */
+int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride, uint32_t flags);
+/* Lower level, for slab overlap: one update restricted to local columns [xa, xb) WITHOUT
+ * flipping the buffers; lbm_flip makes the written buffer current.  slot = force slot. */
+int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot, uint32_t flags);
+int lbm_flip(lbm_t *h);
+
+/* Stream + (I)BB + Zou-He of the current F with wall row `row`, no collision: materialises the
+ * reference's g (nb_col_str stream part + set_bc) in the other buffer, overwrites rho,u on the
+ * walls as the nb_zou_he_* kernels do, and stores the forces in slot 0. */
+int lbm_apply_bc(lbm_t *h, int64_t row);
+
+/* nb_drag_lift numerator: per obstacle (fx, fy) = sum_k (F_q + g_qbar) c_q.  lbm_get_forces
+ * reads slots first..first+n-1 written by the last lbm_step; lbm_forces_now evaluates the
+ * current F directly (what lattice.drag_lift sees right after set_bc).  out: [n][n_obs][2]. */
+int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out);
+int lbm_forces_now(lbm_t *h, double *out);
+
+int lbm_get_populations(lbm_t *h, int32_t which, void *host);
+/* rho[nxl][ny], u[2][nxl][ny] as stored by the last LBM_STEP_MACRO_LAST update (+ wall
+ * overwrites of a later lbm_apply_bc): the composite the reference leaves in lattice.rho/u. */
+int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host);
+
+/* Launch counter: kernels launched by this handle since creation (bench.py gpu_launches). */
+int64_t lbm_launch_count(const lbm_t *h);
+/* Device time of the updates of the last lbm_step call, from CUDA events recorded on the
+ * handle's stream around them (milliseconds; waits for the stream). */
+int lbm_last_step_ms(lbm_t *h, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

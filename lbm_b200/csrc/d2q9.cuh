@@ -1,0 +1,195 @@
+// d2q9.cuh -- per-cell arithmetic of the D2Q9 TRT time step (device side).
+//
+// Restates, for one lattice cell held in registers, what the reference does with whole-array
+// passes: lattice.macro (lbm/src/core/lattice.py:178-189), nb_equilibrium (nb.py:7-17), the
+// collision half of nb_col_str (nb.py:25-35), the five Zou-He wall kernels (nb.py:121-247) and
+// the four corner kernels (nb.py:251-344).  Expression order follows the reference text so that
+// the STRICT arithmetic (no FMA contraction) is bit-identical to oracle/lbm_oracle.c.
+#pragma once
+#include <cstdint>
+
+namespace lbm {
+
+// D2Q9 tables, lattice.py:135-152
+__device__ __constant__ const int kCx[9] = {0, 1, -1, 0, 0, 1, -1, -1, 1};
+__device__ __constant__ const int kCy[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+__host__ __device__ constexpr int opp(int q) { return q == 0 ? 0 : (q & 1 ? q + 1 : q - 1); }
+__host__ __device__ constexpr int cx_of(int q) { return q == 1 || q == 5 || q == 8 ? 1 : (q == 2 || q == 6 || q == 7 ? -1 : 0); }
+__host__ __device__ constexpr int cy_of(int q) { return q == 3 || q == 5 || q == 7 ? 1 : (q == 4 || q == 6 || q == 8 ? -1 : 0); }
+
+// Arithmetic policy.  STRICT: every operation separately rounded (the *_rn intrinsics are never
+// contracted by nvcc).  FUSED: plain operators, nvcc contracts mul+add into FMA (-fmad=true).
+template <typename T, bool STRICT> struct Ar;
+template <> struct Ar<double, true> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+template <> struct Ar<float, true> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <typename T> struct Ar<T, false> {
+    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+    static __device__ __forceinline__ T div(T a, T b) { return a / b; }
+};
+
+template <typename T> struct Coef {
+    T one_m_omp, om_p;        // q = 0:      (1-om_p) g0 + om_p geq0                 nb.py:26
+    T a_self, a_opp, a_eq;    // q >= 1:     1-(om_p+om_m)/2, (om_p-om_m)/2, (om_p+om_m)/2   nb.py:31-35
+};
+
+// rho = sum_q g_q in index order; u = (c . g) / rho     (lattice.py:181-189, oracle orc_macro)
+template <typename A, typename T>
+__device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy)
+{
+    r = A::add(G[0], G[1]);
+#pragma unroll
+    for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
+    T mx = A::add(A::sub(A::sub(A::add(A::sub(G[1], G[2]), G[5]), G[6]), G[7]), G[8]);
+    T my = A::sub(A::add(A::sub(A::add(A::sub(G[3], G[4]), G[5]), G[6]), G[7]), G[8]);
+    ux = A::div(mx, r);
+    uy = A::div(my, r);
+}
+
+// g_eq (nb.py:10-17) followed by the TRT collision (nb.py:25-35); G -> F in place.
+template <typename A, typename T>
+__device__ __forceinline__ void collide(T (&G)[9], T r, T ux, T uy, const Coef<T> &c)
+{
+    const T w0 = T(4.0 / 9.0), w1 = T(1.0 / 9.0), w5 = T(1.0 / 36.0);
+    const T v = A::mul(T(1.5), A::add(A::mul(ux, ux), A::mul(uy, uy)));
+    const T rw0 = A::mul(r, w0), rw1 = A::mul(r, w1), rw5 = A::mul(r, w5);
+    // q = 0: t = 0
+    {
+        T e = A::sub(A::add(A::add(T(1.0), T(0.0)), T(0.0)), v);
+        T geq = A::mul(e, rw0);
+        G[0] = A::add(A::mul(c.one_m_omp, G[0]), A::mul(c.om_p, geq));
+    }
+    // opposite pairs (q, q+1): t_q = 3 c_q.u, t_qbar = -t_q
+    const T s[4] = {ux, uy, A::add(ux, uy), A::sub(uy, ux)};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int q = 2 * k + 1, qb = q + 1;
+        const T rw = k < 2 ? rw1 : rw5;
+        const T t = A::mul(T(3.0), s[k]);
+        const T h = A::mul(T(0.5), A::mul(t, t));
+        const T eq = A::mul(A::sub(A::add(A::add(T(1.0), t), h), v), rw);
+        const T eb = A::mul(A::sub(A::add(A::sub(T(1.0), t), h), v), rw);
+        const T gq = G[q], gb = G[qb];
+        G[q]  = A::add(A::add(A::sub(A::mul(c.a_self, gq), A::mul(c.a_opp, gb)), A::mul(c.a_eq, eq)),
+                       A::mul(c.a_opp, eb));
+        G[qb] = A::add(A::add(A::sub(A::mul(c.a_self, gb), A::mul(c.a_opp, gq)), A::mul(c.a_eq, eb)),
+                       A::mul(c.a_opp, eq));
+    }
+}
+
+// equilibrium only (nb.py:10-17)
+template <typename A, typename T>
+__device__ __forceinline__ void equilibrium(T (&E)[9], T r, T ux, T uy)
+{
+    const T w[3] = {T(4.0 / 9.0), T(1.0 / 9.0), T(1.0 / 36.0)};
+    const T v = A::mul(T(1.5), A::add(A::mul(ux, ux), A::mul(uy, uy)));
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const T cu = A::add(A::mul(ux, T(cx_of(q))), A::mul(uy, T(cy_of(q))));
+        const T t = A::mul(T(3.0), cu);
+        const T e = A::sub(A::add(A::add(T(1.0), t), A::mul(T(0.5), A::mul(t, t))), v);
+        E[q] = A::mul(e, A::mul(r, w[q == 0 ? 0 : (q < 5 ? 1 : 2)]));
+    }
+}
+
+// ---- Zou-He walls -----------------------------------------------------------------------
+// Each fills the three unknown populations of an off-corner wall cell and returns rho/ux/uy as
+// the reference stores them in its rho/u arrays.
+template <typename A, typename T> struct ZouHe {
+    static __device__ __forceinline__ T sum6(T a, T b, T c, T d, T e, T f)
+    {   // a + b + c + 2d + 2e + 2f, left to right
+        return A::add(A::add(A::add(A::add(A::add(a, b), c), A::mul(T(2.0), d)), A::mul(T(2.0), e)),
+                      A::mul(T(2.0), f));
+    }
+    static constexpr double c1 = 2.0 / 3.0, c2 = 1.0 / 6.0, c3 = 0.5;
+
+    // nb.py:121-143
+    static __device__ __forceinline__ void left(T (&G)[9], T ux, T uy, T &r)
+    {
+        r = A::div(sum6(G[0], G[3], G[4], G[2], G[6], G[7]), A::sub(T(1.0), ux));
+        const T d = A::sub(G[3], G[4]);
+        const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
+        G[1] = A::add(G[2], A::mul(k1, ux));
+        G[5] = A::add(A::add(A::sub(G[6], A::mul(T(c3), d)), A::mul(k2, ux)), A::mul(k3, uy));
+        G[8] = A::sub(A::add(A::add(G[7], A::mul(T(c3), d)), A::mul(k2, ux)), A::mul(k3, uy));
+    }
+    // nb.py:147-169 (velocity) and nb.py:173-195 (pressure: rho given, ux solved)
+    static __device__ __forceinline__ void right(T (&G)[9], T &ux, T uy, T &r, bool pressure)
+    {
+        const T s = sum6(G[0], G[3], G[4], G[1], G[5], G[8]);
+        if (pressure) ux = A::sub(A::div(s, r), T(1.0));
+        else          r = A::div(s, A::add(T(1.0), ux));
+        const T d = A::sub(G[3], G[4]);
+        const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
+        G[2] = A::sub(G[1], A::mul(k1, ux));
+        G[6] = A::sub(A::sub(A::add(G[5], A::mul(T(c3), d)), A::mul(k2, ux)), A::mul(k3, uy));
+        G[7] = A::add(A::sub(A::sub(G[8], A::mul(T(c3), d)), A::mul(k2, ux)), A::mul(k3, uy));
+    }
+    // nb.py:199-221
+    static __device__ __forceinline__ T top_rho(T g0, T g1, T g2, T g3, T g5, T g7, T uy)
+    {
+        return A::div(sum6(g0, g1, g2, g3, g5, g7), A::add(T(1.0), uy));
+    }
+    static __device__ __forceinline__ void top(T (&G)[9], T ux, T uy, T &r)
+    {
+        r = top_rho(G[0], G[1], G[2], G[3], G[5], G[7], uy);
+        const T d = A::sub(G[1], G[2]);
+        const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
+        G[4] = A::sub(G[3], A::mul(k1, uy));
+        G[8] = A::sub(A::add(A::sub(G[7], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
+        G[6] = A::sub(A::sub(A::add(G[5], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
+    }
+    // nb.py:225-247
+    static __device__ __forceinline__ T bottom_rho(T g0, T g1, T g2, T g4, T g6, T g8, T uy)
+    {
+        return A::div(sum6(g0, g1, g2, g4, g6, g8), A::sub(T(1.0), uy));
+    }
+    static __device__ __forceinline__ void bottom(T (&G)[9], T ux, T uy, T &r)
+    {
+        r = bottom_rho(G[0], G[1], G[2], G[4], G[6], G[8], uy);
+        const T d = A::sub(G[1], G[2]);
+        const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
+        G[3] = A::add(G[4], A::mul(k1, uy));
+        G[5] = A::add(A::add(A::sub(G[6], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
+        G[7] = A::add(A::sub(A::add(G[8], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
+    }
+    // corners nb.py:251-344; (r, ux, uy) copied from the x-neighbour on the horizontal wall
+    static __device__ __forceinline__ void corner(T (&G)[9], bool is_left, bool is_bottom, T r, T ux, T uy)
+    {
+        const T k23 = A::mul(T(2.0 / 3.0), r), k16 = A::mul(T(1.0 / 6.0), r);
+        if (is_left) G[1] = A::add(G[2], A::mul(k23, ux));
+        else         G[2] = A::sub(G[1], A::mul(k23, ux));
+        if (is_bottom) G[3] = A::add(G[4], A::mul(k23, uy));
+        else           G[4] = A::sub(G[3], A::mul(k23, uy));
+        if (is_left && is_bottom) {
+            G[5] = A::add(A::add(G[6], A::mul(k16, ux)), A::mul(k16, uy));
+            G[7] = T(0.0); G[8] = T(0.0);
+        } else if (is_left) {
+            G[8] = A::sub(A::add(G[7], A::mul(k16, ux)), A::mul(k16, uy));
+            G[5] = T(0.0); G[6] = T(0.0);
+        } else if (!is_bottom) {
+            G[6] = A::sub(A::sub(G[5], A::mul(k16, ux)), A::mul(k16, uy));
+            G[7] = T(0.0); G[8] = T(0.0);
+        } else {
+            G[7] = A::add(A::sub(G[8], A::mul(k16, ux)), A::mul(k16, uy));
+            G[5] = T(0.0); G[6] = T(0.0);
+        }
+        T g0 = A::sub(r, G[1]);
+#pragma unroll
+        for (int q = 2; q < 9; q++) g0 = A::sub(g0, G[q]);
+        G[0] = g0;
+    }
+};
+
+}  // namespace lbm

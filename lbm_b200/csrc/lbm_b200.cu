@@ -1,0 +1,1025 @@
+// lbm_b200.cu -- sm_100a kernels and the C ABI (include/lbm_b200.h) of the D2Q9 time step.
+//
+// One fused kernel per lattice update: pull-stream from the post-collision array F of the
+// previous update, obstacle (interpolated) bounce-back, Zou-He walls/corners, macro,
+// equilibrium, TRT collision, store.  See DESIGN.md for layout and roofline.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "d2q9.cuh"
+
+namespace lbm {
+
+enum Mode { kFused = 0, kCollideOnly = 1, kStreamOnly = 2 };
+
+// ---------------------------------------------------------------------------------------
+// Kernel parameters
+// ---------------------------------------------------------------------------------------
+template <typename T> struct StepParams {
+    const T *src;           // element (q=0, x=0, y=0) of the array read
+    T *dst;                 // same element of the array written
+    long long plane;        // elements between q planes
+    int pitch;              // elements between x columns
+    int nxl, ny;            // local slab width, height
+    int xa, xb;             // local columns processed [xa, xb)
+    long long gx0, gnx;     // global column of local x = 0, global width
+    Coef<T> coef;
+    const T *walls;         // wall row of this update: u_left[2][ny] u_right[2][ny] u_top[2][gnx] u_bot[2][gnx] rho_right[ny]
+    T *rho_out, *u_out;     // optional macro output (pitched [nxl][pitch], [2][nxl][pitch])
+    const unsigned char *mask;  // optional: nonzero = cell is handled by the link blocks
+    int right_pressure;
+    int write_macro;
+};
+
+struct LinkParams {
+    int n_cells;            // distinct boundary cells in this slab
+    int n_links;
+    int n_obs;
+    const int *cell_x, *cell_y, *cell_off;   // [n_cells], [n_cells], [n_cells+1]
+    const int *link_q;                       // [n_links] direction fluid -> solid
+    const int *link_kind;                    // 0 plain BB, 1 IBB p<1/2, 2 IBB p>=1/2
+    const int *link_slot;                    // position in the caller's concatenated list
+    const void *link_c;                      // [n_links][3] coefficients (T)
+    const int *obs_off;                      // [n_obs+1] ranges of the caller's list
+    double *link_f;                          // [n_links_total][2] per-link momentum exchange
+    double *forces;                          // [n_obs][2] output slot
+    unsigned int *done;                      // block completion counter
+    int n_link_blocks;
+};
+
+template <typename T> __device__ __forceinline__ T ldg(const T *p) { return __ldg(p); }
+
+// Pull the nine populations arriving at local cell (x, y).  Entries with no in-domain source
+// are garbage here and are overwritten by the wall code.
+template <typename T>
+__device__ __forceinline__ void pull(const StepParams<T> &p, int x, int y, T (&G)[9])
+{
+    const T *c = p.src + (long long)x * p.pitch + y;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+        G[q] = ldg(c + q * p.plane - cx_of(q) * p.pitch - cy_of(q));
+}
+
+template <typename T>
+__device__ __forceinline__ void load_local(const StepParams<T> &p, int x, int y, T (&G)[9])
+{
+    const T *c = p.src + (long long)x * p.pitch + y;
+#pragma unroll
+    for (int q = 0; q < 9; q++) G[q] = ldg(c + q * p.plane);
+}
+
+// Zou-He density of the off-corner cell (xn, 0) / (xn, ny-1) computed straight from F; used by
+// the corner cells, which copy rho and u from that neighbour (nb.py:254-257 and siblings).
+template <typename A, typename T>
+__device__ __forceinline__ T neighbour_wall_rho(const StepParams<T> &p, int xn, bool bottom, T uy)
+{
+    T G[9];
+    pull(p, xn, bottom ? 0 : p.ny - 1, G);
+    return bottom ? ZouHe<A, T>::bottom_rho(G[0], G[1], G[2], G[4], G[6], G[8], uy)
+                  : ZouHe<A, T>::top_rho(G[0], G[1], G[2], G[3], G[5], G[7], uy);
+}
+
+// Wall / corner treatment of the streamed populations of cell (x, y).  Returns true when the
+// cell is on a wall; then (r, ux, uy) are what the reference writes into rho/u there.
+template <typename A, typename T>
+__device__ __forceinline__ bool apply_walls(const StepParams<T> &p, int x, int y, T (&G)[9], T &r,
+                                            T &ux, T &uy)
+{
+    const long long gx = p.gx0 + x;
+    const bool L = gx == 0, R = gx == p.gnx - 1, B = y == 0, Tp = y == p.ny - 1;
+    if (!(L | R | B | Tp)) return false;
+    const T *ul = p.walls, *ur = ul + 2 * p.ny, *ut = ur + 2 * p.ny, *ub = ut + 2 * p.gnx,
+            *rr = ub + 2 * p.gnx;
+    if ((L | R) & (B | Tp)) {
+        // corner: neighbour on the same horizontal wall
+        const int xn = L ? x + 1 : x - 1;
+        const long long gxn = L ? gx + 1 : gx - 1;
+        const T *uw = B ? ub : ut;
+        ux = uw[gxn];
+        uy = uw[p.gnx + gxn];
+        r = neighbour_wall_rho<A, T>(p, xn, B, uy);
+        ZouHe<A, T>::corner(G, L, B, r, ux, uy);
+    } else if (B) {
+        ux = ub[gx]; uy = ub[p.gnx + gx];
+        ZouHe<A, T>::bottom(G, ux, uy, r);
+    } else if (Tp) {
+        ux = ut[gx]; uy = ut[p.gnx + gx];
+        ZouHe<A, T>::top(G, ux, uy, r);
+    } else if (L) {
+        ux = ul[y]; uy = ul[p.ny + y];
+        ZouHe<A, T>::left(G, ux, uy, r);
+    } else {
+        ux = ur[y]; uy = ur[p.ny + y];
+        r = rr[y];  // only used by the pressure variant
+        ZouHe<A, T>::right(G, ux, uy, r, p.right_pressure != 0);
+    }
+    return true;
+}
+
+// Everything after the populations of a cell are in registers: walls, macro, collision, store.
+template <typename T, bool STRICT, int MODE>
+__device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y, T (&G)[9])
+{
+    using A = Ar<T, STRICT>;
+    const long long cell = (long long)x * p.pitch + y;
+    if (MODE != kCollideOnly) {
+        T r, ux, uy;
+        const bool on_wall = apply_walls<A, T>(p, x, y, G, r, ux, uy);
+        if (MODE == kStreamOnly) {
+            if (on_wall && p.rho_out) {
+                p.rho_out[cell] = r;
+                p.u_out[cell] = ux;
+                p.u_out[(long long)p.nxl * p.pitch + cell] = uy;
+            }
+        }
+    }
+    if (MODE != kStreamOnly) {
+        T r, ux, uy;
+        macro<A, T>(G, r, ux, uy);
+        if (p.write_macro) {
+            p.rho_out[cell] = r;
+            p.u_out[cell] = ux;
+            p.u_out[(long long)p.nxl * p.pitch + cell] = uy;
+        }
+        collide<A, T>(G, r, ux, uy, p.coef);
+    }
+    T *d = p.dst + cell;
+#pragma unroll
+    for (int q = 0; q < 9; q++) d[q * p.plane] = G[q];
+}
+
+// ---------------------------------------------------------------------------------------
+// Obstacle links: one thread per distinct boundary cell (the extra blocks of the step kernel)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
+__device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
+{
+    using A = Ar<T, STRICT>;
+    const int c = block * nthreads + threadIdx.x;
+    if (c < lp.n_cells) {
+        const int x = lp.cell_x[c], y = lp.cell_y[c];
+        T G[9];
+        if (!FORCE_ONLY) pull(p, x, y, G);
+        const T *ctr = p.src + (long long)x * p.pitch + y;
+        const T *coef = static_cast<const T *>(lp.link_c);
+        for (int l = lp.cell_off[c]; l < lp.cell_off[c + 1]; l++) {
+            const int q = lp.link_q[l], qb = opp(q), kind = lp.link_kind[l];
+            const int cbx = kCx[qb], cby = kCy[qb];
+            const long long o1 = (long long)cbx * p.pitch + cby;   // (im, jm) = (i, j) + c_qbar
+            const T *Fq = ctr + q * p.plane, *Fb = ctr + qb * p.plane;
+            const T a = ldg(Fq);
+            const T c0 = coef[3 * l], c1 = coef[3 * l + 1], c2 = coef[3 * l + 2];
+            T val;
+            if (kind == 1)        // nb.py:98-100
+                val = A::sub(A::add(A::mul(c0, a), A::mul(c1, ldg(Fq + o1))), A::mul(c2, ldg(Fq + 2 * o1)));
+            else if (kind == 2)   // nb.py:102-104
+                val = A::add(A::add(A::mul(c0, a), A::mul(c1, ldg(Fb))), A::mul(c2, ldg(Fb + o1)));
+            else                  // nb.py:117
+                val = a;
+            if (!FORCE_ONLY) {
+#pragma unroll
+                for (int k = 1; k < 9; k++)
+                    if (k == qb) G[k] = val;
+            }
+            // nb.py:64-67: (g_up_q + g_qbar) c_q
+            const T g0 = A::add(a, val);
+            const int s = lp.link_slot[l];
+            lp.link_f[2 * s] = (double)A::mul(g0, T(kCx[q]));
+            lp.link_f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
+        }
+        if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
+    }
+    // last block done: fixed-order reduction of the per-link terms, per obstacle
+    __shared__ bool last;
+    __shared__ double red[2][256];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int o = 0; o < lp.n_obs; o++) {
+        double fx = 0.0, fy = 0.0;
+        for (int k = lp.obs_off[o] + threadIdx.x; k < lp.obs_off[o + 1]; k += nthreads) {
+            fx += __ldcg(lp.link_f + 2 * k);
+            fy += __ldcg(lp.link_f + 2 * k + 1);
+        }
+        red[0][threadIdx.x] = fx;
+        red[1][threadIdx.x] = fy;
+        __syncthreads();
+        for (int s = nthreads / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                red[0][threadIdx.x] += red[0][threadIdx.x + s];
+                red[1][threadIdx.x] += red[1][threadIdx.x + s];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            lp.forces[2 * o] = red[0][0];
+            lp.forces[2 * o + 1] = red[1][0];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *lp.done = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// The step kernel.  grid.x = y tiles, grid.y = local columns xa..xb-1 (+ link blocks appended
+// along grid.y when obstacles are present); one thread per cell, threadIdx.x along y (the
+// contiguous axis) so every population plane is read and written as full 128 B lines.
+// ---------------------------------------------------------------------------------------
+constexpr int kBlock = 256;
+
+template <typename T, bool STRICT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
+{
+    const int ncols = p.xb - p.xa;
+    if ((int)blockIdx.y >= ncols) {
+        if (MODE != kCollideOnly) {
+            const int b = ((int)blockIdx.y - ncols) * gridDim.x + blockIdx.x;
+            if (b < lp.n_link_blocks) link_block<T, STRICT, MODE, false>(p, lp, b, kBlock);
+        }
+        return;
+    }
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = p.xa + blockIdx.y;
+    if (y >= p.ny) return;
+    if (MODE != kCollideOnly && p.mask && p.mask[(long long)x * p.pitch + y]) return;
+    T G[9];
+    if (MODE == kCollideOnly) load_local(p, x, y, G);
+    else pull(p, x, y, G);
+    finish_cell<T, STRICT, MODE>(p, x, y, G);
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+force_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
+{
+    link_block<T, STRICT, kFused, true>(p, lp, blockIdx.x, kBlock);
+}
+
+// uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+init_kernel(T *dst, long long plane, int pitch, int nxl, int ny, T r, T ux, T uy)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = blockIdx.y;
+    if (y >= ny) return;
+    T E[9];
+    equilibrium<Ar<T, STRICT>, T>(E, r, ux, uy);
+#pragma unroll
+    for (int q = 0; q < 9; q++) dst[q * plane + (long long)x * pitch + y] = E[q];
+}
+
+// nb_equilibrium on pitched device fields
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+equilibrium_kernel(T *dst, long long plane, int pitch, int nxl, int ny, const T *rho, const T *u)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = blockIdx.y;
+    if (y >= ny) return;
+    const long long cell = (long long)x * pitch + y;
+    T E[9];
+    equilibrium<Ar<T, STRICT>, T>(E, rho[cell], u[cell], u[(long long)nxl * pitch + cell]);
+#pragma unroll
+    for (int q = 0; q < 9; q++) dst[q * plane + cell] = E[q];
+}
+
+}  // namespace lbm
+
+// =========================================================================================
+// Host side: handle + C ABI
+// =========================================================================================
+using namespace lbm;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? LBM_E_NOMEM : LBM_E_CUDA, "%s: %s",   \
+                        #expr, cudaGetErrorString(e_));                                         \
+    } while (0)
+
+enum StateKind { kNone = 0, kHaveG = 1, kHaveF = 2 };
+
+struct lbm_handle {
+    lbm_cfg cfg;
+    lbm_layout lay;
+    size_t esz;
+    void *buf[2] = {nullptr, nullptr};
+    bool own_buf = false;
+    int cur = 0;
+    StateKind kind = kNone;
+    bool other_has_g = false;     // other buffer holds stream+BC of current F (lbm_apply_bc)
+    cudaStream_t stream = nullptr;
+    // walls
+    void *walls = nullptr;        // device table, element type T
+    int64_t wall_rows = 0, wall_cap = 0, row_len = 0;
+    // macro
+    void *rho = nullptr, *u = nullptr;
+    bool macro_valid = false;
+    // links
+    int n_obs = 0, n_cells = 0, n_links = 0, n_links_total = 0, n_link_blocks = 0;
+    int *d_cell_x = nullptr, *d_cell_y = nullptr, *d_cell_off = nullptr, *d_link_q = nullptr,
+        *d_link_kind = nullptr, *d_link_slot = nullptr, *d_obs_off = nullptr;
+    void *d_link_c = nullptr;
+    double *d_link_f = nullptr;
+    unsigned int *d_done = nullptr;
+    unsigned char *d_mask = nullptr;
+    // forces
+    double *d_forces = nullptr;
+    int64_t force_cap = 0, force_n = 0;
+    // accounting
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static void compute_layout(const lbm_cfg &c, lbm_layout &l)
+{
+    l.elem_size = c.dtype == LBM_F64 ? 8 : 4;
+    l.pitch = round_up(c.ny, 128 / l.elem_size);
+    l.plane = (c.nxl + 2) * l.pitch;
+    // one guard column before and after everything so that y-1 / y+1 pulls at the first and
+    // last halo column stay inside the allocation
+    l.origin = l.pitch /*guard*/ + l.pitch /*halo column x = -1*/;
+    l.elems = 9 * l.plane + 2 * l.pitch;
+}
+
+static int check_cfg(const lbm_cfg *c)
+{
+    if (!c) return fail(LBM_E_INVALID, "cfg is NULL");
+    if (c->nx < 3 || c->ny < 3) return fail(LBM_E_INVALID, "lattice must be at least 3x3 (got %lld x %lld)", (long long)c->nx, (long long)c->ny);
+    if (c->ny > (1 << 30) || c->nx > (1LL << 31) - 2) return fail(LBM_E_INVALID, "lattice too large");
+    if (c->x0 < 0 || c->nxl < 1 || c->x0 + c->nxl > c->nx) return fail(LBM_E_INVALID, "slab [%lld, %lld) outside [0, %lld)", (long long)c->x0, (long long)(c->x0 + c->nxl), (long long)c->nx);
+    if (c->nxl < 2 && c->nxl != c->nx) return fail(LBM_E_INVALID, "slab must be at least 2 columns wide");
+    if (c->dtype != LBM_F64 && c->dtype != LBM_F32) return fail(LBM_E_INVALID, "dtype must be LBM_F64 or LBM_F32");
+    if (c->arith != LBM_ARITH_FUSED && c->arith != LBM_ARITH_STRICT) return fail(LBM_E_INVALID, "bad arith");
+    if (c->right_wall != LBM_RIGHT_VELOCITY && c->right_wall != LBM_RIGHT_PRESSURE) return fail(LBM_E_INVALID, "bad right_wall");
+    if (!(c->om_p > 0.0) || !(c->om_m > 0.0)) return fail(LBM_E_INVALID, "relaxation rates must be positive");
+    return LBM_OK;
+}
+
+#define CHECK_H(h) do { if (!(h)) return fail(LBM_E_INVALID, "handle is NULL"); CUDA_TRY(cudaSetDevice((h)->cfg.device)); } while (0)
+
+static void *elem_ptr(const lbm_handle *h, int which, int64_t off)
+{
+    return static_cast<char *>(h->buf[which]) + (h->lay.origin + off) * h->esz;
+}
+
+static int ensure_state(lbm_handle *h)
+{
+    if (h->buf[0]) return LBM_OK;
+    const size_t bytes = (size_t)h->lay.elems * h->esz;
+    CUDA_TRY(cudaMalloc(&h->buf[0], bytes));
+    CUDA_TRY(cudaMalloc(&h->buf[1], bytes));
+    h->own_buf = true;
+    CUDA_TRY(cudaMemsetAsync(h->buf[0], 0, bytes, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->buf[1], 0, bytes, h->stream));
+    return LBM_OK;
+}
+
+static int ensure_macro(lbm_handle *h)
+{
+    if (h->rho) return LBM_OK;
+    const size_t n = (size_t)h->cfg.nxl * h->lay.pitch * h->esz;
+    CUDA_TRY(cudaMalloc(&h->rho, n));
+    CUDA_TRY(cudaMalloc(&h->u, 2 * n));
+    CUDA_TRY(cudaMemsetAsync(h->rho, 0, n, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->u, 0, 2 * n, h->stream));
+    return LBM_OK;
+}
+
+static int ensure_forces(lbm_handle *h, int64_t n)
+{
+    const int nobs = std::max(h->n_obs, 1);
+    if (h->d_forces && h->force_cap >= n) return LBM_OK;
+    if (h->d_forces) { CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->d_forces)); h->d_forces = nullptr; }
+    const int64_t cap = std::max<int64_t>(n, 64);
+    CUDA_TRY(cudaMalloc(&h->d_forces, (size_t)cap * nobs * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(h->d_forces, 0, (size_t)cap * nobs * 2 * sizeof(double), h->stream));
+    h->force_cap = cap;
+    return LBM_OK;
+}
+
+template <typename T> static void fill_params(const lbm_handle *h, StepParams<T> &p, LinkParams &lp,
+                                               int src, int dst, int xa, int xb, int64_t row, int64_t slot)
+{
+    p.src = static_cast<const T *>(elem_ptr(h, src, 0));
+    p.dst = static_cast<T *>(elem_ptr(h, dst, 0));
+    p.plane = h->lay.plane;
+    p.pitch = (int)h->lay.pitch;
+    p.nxl = (int)h->cfg.nxl;
+    p.ny = (int)h->cfg.ny;
+    p.xa = xa;
+    p.xb = xb;
+    p.gx0 = h->cfg.x0;
+    p.gnx = h->cfg.nx;
+    const double op = h->cfg.om_p, om = h->cfg.om_m;
+    p.coef.one_m_omp = T(1.0 - op);
+    p.coef.om_p = T(op);
+    p.coef.a_self = T(1.0 - 0.5 * (op + om));
+    p.coef.a_opp = T(0.5 * (op - om));
+    p.coef.a_eq = T(0.5 * (op + om));
+    p.walls = h->walls ? static_cast<const T *>(h->walls) + row * h->row_len : nullptr;
+    p.rho_out = static_cast<T *>(h->rho);
+    p.u_out = static_cast<T *>(h->u);
+    p.mask = h->d_mask;
+    p.right_pressure = h->cfg.right_wall == LBM_RIGHT_PRESSURE;
+    p.write_macro = 0;
+    lp.n_cells = h->n_cells;
+    lp.n_links = h->n_links;
+    lp.n_obs = h->n_obs;
+    lp.cell_x = h->d_cell_x; lp.cell_y = h->d_cell_y; lp.cell_off = h->d_cell_off;
+    lp.link_q = h->d_link_q; lp.link_kind = h->d_link_kind; lp.link_slot = h->d_link_slot;
+    lp.link_c = h->d_link_c;
+    lp.obs_off = h->d_obs_off;
+    lp.link_f = h->d_link_f;
+    lp.forces = h->d_forces ? h->d_forces + slot * std::max(h->n_obs, 1) * 2 : nullptr;
+    lp.done = h->d_done;
+    lp.n_link_blocks = h->n_link_blocks;
+}
+
+template <typename T, bool STRICT>
+static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int xb, int64_t row,
+                         int64_t slot, bool write_macro)
+{
+    StepParams<T> p;
+    LinkParams lp;
+    fill_params<T>(h, p, lp, src, dst, xa, xb, row, slot);
+    p.write_macro = write_macro ? 1 : 0;
+    const int ytiles = (int)((h->cfg.ny + kBlock - 1) / kBlock);
+    int extra = 0;
+    // link blocks ride along only when the whole slab is processed by this launch
+    const bool links_here = mode != kCollideOnly && h->n_link_blocks > 0 && xa == 0 && xb == (int)h->cfg.nxl;
+    if (links_here) extra = (h->n_link_blocks + ytiles - 1) / ytiles;
+    else lp.n_link_blocks = 0;
+    if (mode != kCollideOnly && h->n_link_blocks > 0 && !links_here)
+        return fail(LBM_E_UNSUPPORTED, "column-restricted updates with obstacles are not supported yet");
+    dim3 grid(ytiles, (xb - xa) + extra), block(kBlock);
+    if (grid.y > 65535) {
+        // grid.y is limited to 65535: split wide slabs into several launches
+        for (int a = xa; a < xb; a += 32768) {
+            const int b = std::min(xb, a + 32768);
+            if (links_here) return fail(LBM_E_UNSUPPORTED, "obstacles on slabs wider than 65535 columns");
+            int rc = launch_step_t<T, STRICT>(h, mode, src, dst, a, b, row, slot, write_macro);
+            if (rc) return rc;
+        }
+        return LBM_OK;
+    }
+    switch (mode) {
+    case kFused: step_kernel<T, STRICT, kFused><<<grid, block, 0, h->stream>>>(p, lp); break;
+    case kCollideOnly: step_kernel<T, STRICT, kCollideOnly><<<grid, block, 0, h->stream>>>(p, lp); break;
+    default: step_kernel<T, STRICT, kStreamOnly><<<grid, block, 0, h->stream>>>(p, lp); break;
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+static int launch_step(lbm_handle *h, int mode, int src, int dst, int xa, int xb, int64_t row,
+                       int64_t slot, bool write_macro)
+{
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    if (h->cfg.dtype == LBM_F64)
+        return strict ? launch_step_t<double, true>(h, mode, src, dst, xa, xb, row, slot, write_macro)
+                      : launch_step_t<double, false>(h, mode, src, dst, xa, xb, row, slot, write_macro);
+    return strict ? launch_step_t<float, true>(h, mode, src, dst, xa, xb, row, slot, write_macro)
+                  : launch_step_t<float, false>(h, mode, src, dst, xa, xb, row, slot, write_macro);
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+const char *lbm_last_error(void) { return g_err.c_str(); }
+
+int lbm_create(const lbm_cfg *cfg, lbm_t **out)
+{
+    if (!out) return fail(LBM_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(LBM_E_INVALID, "device %d not present (%d visible)", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    lbm_handle *h = new (std::nothrow) lbm_handle();
+    if (!h) return fail(LBM_E_NOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    compute_layout(*cfg, h->lay);
+    h->esz = (size_t)h->lay.elem_size;
+    h->row_len = 5 * cfg->ny + 4 * cfg->nx;
+    cudaError_t e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) { delete h; return fail(LBM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return LBM_OK;
+}
+
+static void free_links(lbm_handle *h)
+{
+    void *ptrs[] = {h->d_cell_x, h->d_cell_y, h->d_cell_off, h->d_link_q, h->d_link_kind, h->d_link_slot,
+                    h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    h->d_cell_x = h->d_cell_y = h->d_cell_off = h->d_link_q = h->d_link_kind = h->d_link_slot = h->d_obs_off = nullptr;
+    h->d_link_c = nullptr; h->d_link_f = nullptr; h->d_done = nullptr; h->d_mask = nullptr;
+    h->n_obs = h->n_cells = h->n_links = h->n_links_total = h->n_link_blocks = 0;
+}
+
+int lbm_destroy(lbm_t *h)
+{
+    if (!h) return LBM_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_buf) { cudaFree(h->buf[0]); cudaFree(h->buf[1]); }
+    if (h->walls) cudaFree(h->walls);
+    if (h->rho) cudaFree(h->rho);
+    if (h->u) cudaFree(h->u);
+    if (h->d_forces) cudaFree(h->d_forces);
+    free_links(h);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return LBM_OK;
+}
+
+int lbm_get_layout(const lbm_t *h, lbm_layout *out)
+{
+    if (!h || !out) return fail(LBM_E_INVALID, "NULL argument");
+    *out = h->lay;
+    return LBM_OK;
+}
+
+int lbm_bind_state(lbm_t *h, void *dev_a, void *dev_b, size_t bytes_each)
+{
+    CHECK_H(h);
+    if (h->buf[0]) return fail(LBM_E_STATE, "state buffers already present");
+    const size_t need = (size_t)h->lay.elems * h->esz;
+    if (!dev_a || !dev_b || dev_a == dev_b) return fail(LBM_E_INVALID, "need two distinct device buffers");
+    if (bytes_each < need) return fail(LBM_E_INVALID, "buffers too small: %zu < %zu bytes", bytes_each, need);
+    if (((uintptr_t)dev_a | (uintptr_t)dev_b) & 127) return fail(LBM_E_INVALID, "buffers must be 128-byte aligned");
+    h->buf[0] = dev_a;
+    h->buf[1] = dev_b;
+    h->own_buf = false;
+    CUDA_TRY(cudaMemsetAsync(dev_a, 0, need, h->stream));
+    CUDA_TRY(cudaMemsetAsync(dev_b, 0, need, h->stream));
+    return LBM_OK;
+}
+
+int lbm_state_ptrs(const lbm_t *h, void **current, void **other)
+{
+    if (!h) return fail(LBM_E_INVALID, "handle is NULL");
+    if (current) *current = h->buf[h->cur];
+    if (other) *other = h->buf[h->cur ^ 1];
+    return LBM_OK;
+}
+
+int lbm_set_stream(lbm_t *h, void *cuda_stream)
+{
+    CHECK_H(h);
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return LBM_OK;
+}
+
+int lbm_set_right_wall(lbm_t *h, int32_t right_wall)
+{
+    CHECK_H(h);
+    if (right_wall != LBM_RIGHT_VELOCITY && right_wall != LBM_RIGHT_PRESSURE) return fail(LBM_E_INVALID, "bad right_wall");
+    h->cfg.right_wall = right_wall;
+    return LBM_OK;
+}
+
+int lbm_sync(lbm_t *h)
+{
+    CHECK_H(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+static int copy_field_h2d(lbm_handle *h, void *dev_cell0, int64_t dev_plane, const void *host, int nplanes)
+{
+    const size_t w = (size_t)h->cfg.ny * h->esz;
+    for (int q = 0; q < nplanes; q++)
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(dev_cell0) + q * dev_plane * h->esz, h->lay.pitch * h->esz,
+                                   static_cast<const char *>(host) + (size_t)q * h->cfg.nxl * w, w, w,
+                                   (size_t)h->cfg.nxl, cudaMemcpyHostToDevice, h->stream));
+    return LBM_OK;
+}
+
+static int copy_field_d2h(lbm_handle *h, const void *dev_cell0, int64_t dev_plane, void *host, int nplanes)
+{
+    const size_t w = (size_t)h->cfg.ny * h->esz;
+    for (int q = 0; q < nplanes; q++)
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(host) + (size_t)q * h->cfg.nxl * w, w,
+                                   static_cast<const char *>(dev_cell0) + q * dev_plane * h->esz, h->lay.pitch * h->esz,
+                                   w, (size_t)h->cfg.nxl, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_set_populations(lbm_t *h, const void *g_host)
+{
+    CHECK_H(h);
+    if (!g_host) return fail(LBM_E_INVALID, "g_host is NULL");
+    int rc = ensure_state(h);
+    if (rc) return rc;
+    rc = copy_field_h2d(h, elem_ptr(h, h->cur, 0), h->lay.plane, g_host, 9);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may free g_host on return
+    h->kind = kHaveG;
+    h->other_has_g = false;
+    h->macro_valid = false;
+    return LBM_OK;
+}
+
+int lbm_init_equilibrium(lbm_t *h, double rho, double ux, double uy)
+{
+    CHECK_H(h);
+    int rc = ensure_state(h);
+    if (rc) return rc;
+    dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), 1), block(kBlock);
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    for (int64_t a = 0; a < h->cfg.nxl; a += 32768) {
+        grid.y = (unsigned)std::min<int64_t>(32768, h->cfg.nxl - a);
+        const int64_t off = a * h->lay.pitch;
+        if (h->cfg.dtype == LBM_F64) {
+            double *d = static_cast<double *>(elem_ptr(h, h->cur, off));
+            if (strict) init_kernel<double, true><<<grid, block, 0, h->stream>>>(d, h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, rho, ux, uy);
+            else init_kernel<double, false><<<grid, block, 0, h->stream>>>(d, h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, rho, ux, uy);
+        } else {
+            float *d = static_cast<float *>(elem_ptr(h, h->cur, off));
+            if (strict) init_kernel<float, true><<<grid, block, 0, h->stream>>>(d, h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, (float)rho, (float)ux, (float)uy);
+            else init_kernel<float, false><<<grid, block, 0, h->stream>>>(d, h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, (float)rho, (float)ux, (float)uy);
+        }
+        h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->kind = kHaveG;
+    h->other_has_g = false;
+    h->macro_valid = false;
+    return LBM_OK;
+}
+
+int lbm_equilibrium(lbm_t *h, const void *rho_host, const void *u_host, void *g_eq_host)
+{
+    CHECK_H(h);
+    if (!rho_host || !u_host || !g_eq_host) return fail(LBM_E_INVALID, "NULL argument");
+    if (h->cfg.nxl > 65535) return fail(LBM_E_UNSUPPORTED, "lbm_equilibrium: slab wider than 65535 columns");
+    // scratch: rho/u device fields + a 9-plane pitched buffer
+    const size_t cells = (size_t)h->cfg.nxl * h->lay.pitch;
+    void *d_rho = nullptr, *d_u = nullptr, *d_g = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rho, cells * h->esz));
+    CUDA_TRY(cudaMalloc(&d_u, 2 * cells * h->esz));
+    CUDA_TRY(cudaMalloc(&d_g, 9 * cells * h->esz));
+    int rc = copy_field_h2d(h, d_rho, (int64_t)cells, rho_host, 1);
+    if (!rc) rc = copy_field_h2d(h, d_u, (int64_t)cells, u_host, 2);
+    if (!rc) {
+        dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)h->cfg.nxl), block(kBlock);
+        const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+        const int pitch = (int)h->lay.pitch, nxl = (int)h->cfg.nxl, ny = (int)h->cfg.ny;
+        if (h->cfg.dtype == LBM_F64) {
+            if (strict) equilibrium_kernel<double, true><<<grid, block, 0, h->stream>>>((double *)d_g, (long long)cells, pitch, nxl, ny, (const double *)d_rho, (const double *)d_u);
+            else equilibrium_kernel<double, false><<<grid, block, 0, h->stream>>>((double *)d_g, (long long)cells, pitch, nxl, ny, (const double *)d_rho, (const double *)d_u);
+        } else {
+            if (strict) equilibrium_kernel<float, true><<<grid, block, 0, h->stream>>>((float *)d_g, (long long)cells, pitch, nxl, ny, (const float *)d_rho, (const float *)d_u);
+            else equilibrium_kernel<float, false><<<grid, block, 0, h->stream>>>((float *)d_g, (long long)cells, pitch, nxl, ny, (const float *)d_rho, (const float *)d_u);
+        }
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "equilibrium_kernel: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = copy_field_d2h(h, d_g, (int64_t)cells, g_eq_host, 9);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_rho); cudaFree(d_u); cudaFree(d_g);
+    return rc;
+}
+
+int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const int64_t *ijq,
+                  const double *ibb, int32_t use_ibb)
+{
+    CHECK_H(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    free_links(h);
+    if (h->d_forces) { cudaFree(h->d_forces); h->d_forces = nullptr; h->force_cap = 0; }
+    if (n_obstacles <= 0) return LBM_OK;
+    if (!offsets || !ijq) return fail(LBM_E_INVALID, "NULL link arrays");
+    if (use_ibb && !ibb) return fail(LBM_E_INVALID, "use_ibb set but ibb is NULL");
+    const int64_t K = offsets[n_obstacles];
+    if (offsets[0] != 0 || K < 0 || K > (1 << 28)) return fail(LBM_E_INVALID, "bad offsets");
+    const int64_t nx = h->cfg.nx, ny = h->cfg.ny, x0 = h->cfg.x0, nxl = h->cfg.nxl;
+    struct L { int x, y, q, kind, slot; double c[3]; };
+    std::vector<L> links;
+    links.reserve((size_t)K);
+    for (int64_t k = 0; k < K; k++) {
+        const int64_t i = ijq[3 * k], j = ijq[3 * k + 1], q = ijq[3 * k + 2];
+        if (q < 1 || q > 8) return fail(LBM_E_INVALID, "link %lld: direction %lld not in 1..8", (long long)k, (long long)q);
+        if (i < 0 || i >= nx || j < 0 || j >= ny)
+            return fail(LBM_E_INVALID, "link %lld: node (%lld, %lld) outside the lattice (the reference wraps negative indices; this library rejects them)", (long long)k, (long long)i, (long long)j);
+        L l;
+        l.q = (int)q; l.slot = (int)k; l.kind = 0; l.c[0] = l.c[1] = l.c[2] = 0.0;
+        if (use_ibb) {
+            const int qb = opp((int)q);
+            const int64_t reach = 2;  // (i, j) + 2 c_qbar is read when p < 1/2, + c_qbar otherwise
+            const double p = ibb[k], pp = 2.0 * p;
+            const int64_t r = p < 0.5 ? reach : 1;
+            const int64_t ie = i + r * cx_of(qb), je = j + r * cy_of(qb);
+            if (ie < 0 || ie >= nx || je < 0 || je >= ny)
+                return fail(LBM_E_INVALID, "link %lld: IBB stencil leaves the lattice", (long long)k);
+            if (p < 0.5) {  // nb.py:98-100
+                l.kind = 1;
+                l.c[0] = p * (pp + 1.0);
+                l.c[1] = (1.0 + pp) * (1.0 - pp);
+                l.c[2] = p * (1.0 - pp);
+            } else {        // nb.py:102-104
+                l.kind = 2;
+                l.c[0] = 1.0 / (p * (pp + 1.0));
+                l.c[1] = (pp - 1.0) / p;
+                l.c[2] = (1.0 - pp) / (1.0 + pp);
+            }
+            if (i >= x0 && i < x0 + nxl) {
+                const int64_t il = ie - x0;
+                if (il < -1 || il > nxl)
+                    return fail(LBM_E_UNSUPPORTED, "link %lld: IBB stencil reaches beyond the one-column slab halo", (long long)k);
+            }
+        }
+        if (i < x0 || i >= x0 + nxl) continue;  // owned by another slab
+        l.x = (int)(i - x0);
+        l.y = (int)j;
+        links.push_back(l);
+    }
+    h->n_obs = n_obstacles;
+    h->n_links_total = (int)K;
+    // group by cell, keeping the caller's order inside a cell (later links overwrite earlier ones)
+    std::vector<int> order(links.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return links[a].x != links[b].x ? links[a].x < links[b].x : links[a].y < links[b].y;
+    });
+    std::vector<int> cx, cy, coff, lq, lkind, lslot;
+    std::vector<double> lc;
+    for (size_t n = 0; n < order.size(); n++) {
+        const L &l = links[order[n]];
+        if (cx.empty() || cx.back() != l.x || cy.back() != l.y) {
+            cx.push_back(l.x); cy.push_back(l.y); coff.push_back((int)n);
+        }
+        lq.push_back(l.q); lkind.push_back(l.kind); lslot.push_back(l.slot);
+        lc.push_back(l.c[0]); lc.push_back(l.c[1]); lc.push_back(l.c[2]);
+    }
+    coff.push_back((int)order.size());
+    h->n_cells = (int)cx.size();
+    h->n_links = (int)order.size();
+    h->n_link_blocks = std::max(1, (h->n_cells + kBlock - 1) / kBlock);  // >= 1 so that forces are always written
+    std::vector<int> obs_off(n_obstacles + 1);
+    for (int o = 0; o <= n_obstacles; o++) obs_off[o] = (int)offsets[o];
+
+    auto up = [&](auto **dptr, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void **)dptr, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    CUDA_TRY(up(&h->d_cell_x, cx.data(), cx.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_cell_y, cy.data(), cy.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_cell_off, coff.data(), coff.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_link_q, lq.data(), lq.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_link_kind, lkind.data(), lkind.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_link_slot, lslot.data(), lslot.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_obs_off, obs_off.data(), obs_off.size() * sizeof(int)));
+    if (h->cfg.dtype == LBM_F64) {
+        CUDA_TRY(up(&h->d_link_c, lc.data(), lc.size() * sizeof(double)));
+    } else {
+        std::vector<float> lcf(lc.begin(), lc.end());
+        CUDA_TRY(up(&h->d_link_c, lcf.data(), lcf.size() * sizeof(float)));
+    }
+    CUDA_TRY(cudaMalloc(&h->d_link_f, std::max<size_t>((size_t)K, 1) * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemset(h->d_link_f, 0, std::max<size_t>((size_t)K, 1) * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_done, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(h->d_done, 0, sizeof(unsigned int)));
+    // per-cell mask: cells owned by the link blocks are skipped by the bulk threads
+    const size_t mbytes = (size_t)nxl * h->lay.pitch;
+    std::vector<unsigned char> mask(mbytes, 0);
+    for (size_t c = 0; c < cx.size(); c++) mask[(size_t)cx[c] * h->lay.pitch + cy[c]] = 1;
+    CUDA_TRY(up(&h->d_mask, mask.data(), mbytes));
+    return LBM_OK;
+}
+
+int64_t lbm_wall_row_len(const lbm_t *h) { return h ? h->row_len : 0; }
+
+int lbm_set_walls(lbm_t *h, int64_t n_rows, const double *rows_host)
+{
+    CHECK_H(h);
+    if (n_rows < 1 || !rows_host) return fail(LBM_E_INVALID, "need at least one wall row");
+    if (n_rows > h->wall_cap) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->walls) CUDA_TRY(cudaFree(h->walls));
+        h->walls = nullptr;
+        h->wall_cap = 0;
+        CUDA_TRY(cudaMalloc(&h->walls, (size_t)n_rows * h->row_len * h->esz));
+        h->wall_cap = n_rows;
+    }
+    const size_t n = (size_t)n_rows * h->row_len;
+    if (h->cfg.dtype == LBM_F64) {
+        CUDA_TRY(cudaMemcpyAsync(h->walls, rows_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        std::vector<float> tmp(n);
+        for (size_t k = 0; k < n; k++) tmp[k] = (float)rows_host[k];
+        CUDA_TRY(cudaMemcpyAsync(h->walls, tmp.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->wall_rows = n_rows;
+    return LBM_OK;
+}
+
+static int check_row(lbm_handle *h, int64_t row)
+{
+    if (!h->walls || row < 0 || row >= h->wall_rows)
+        return fail(LBM_E_INVALID, "wall row %lld not in the table (%lld rows set)", (long long)row, (long long)h->wall_rows);
+    return LBM_OK;
+}
+
+int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride, uint32_t flags)
+{
+    CHECK_H(h);
+    if (n_updates < 0) return fail(LBM_E_INVALID, "n_updates < 0");
+    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
+    if (n_updates == 0) return LBM_OK;
+    int rc = ensure_forces(h, n_updates);
+    if (rc) return rc;
+    if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
+    // validate the rows before enqueuing anything
+    for (int64_t s = 0; s < n_updates; s++) {
+        if (s == 0 && h->kind == kHaveG) continue;  // collide-only update uses no walls
+        rc = check_row(h, first_row + s * row_stride);
+        if (rc) return rc;
+        if (row_stride == 0) break;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int64_t s = 0; s < n_updates; s++) {
+        const bool last = s == n_updates - 1;
+        const bool wm = last && (flags & LBM_STEP_MACRO_LAST);
+        const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
+        rc = launch_step(h, mode, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride, s, wm);
+        if (rc) return rc;
+        h->cur ^= 1;
+        h->kind = kHaveF;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    h->ev_valid = true;
+    h->force_n = n_updates;
+    h->other_has_g = false;
+    if (flags & LBM_STEP_MACRO_LAST) h->macro_valid = true;
+    return LBM_OK;
+}
+
+int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot, uint32_t flags)
+{
+    CHECK_H(h);
+    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
+    if (xa < 0 || xb > h->cfg.nxl || xa >= xb) return fail(LBM_E_INVALID, "bad column range");
+    int rc = ensure_forces(h, slot + 1);
+    if (rc) return rc;
+    if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
+    const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
+    if (mode == kFused) { rc = check_row(h, row); if (rc) return rc; }
+    return launch_step(h, mode, h->cur, h->cur ^ 1, (int)xa, (int)xb, row, slot, (flags & LBM_STEP_MACRO_LAST) != 0);
+}
+
+int lbm_flip(lbm_t *h)
+{
+    CHECK_H(h);
+    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
+    h->cur ^= 1;
+    h->kind = kHaveF;
+    h->other_has_g = false;
+    return LBM_OK;
+}
+
+int lbm_apply_bc(lbm_t *h, int64_t row)
+{
+    CHECK_H(h);
+    if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_apply_bc needs post-collision populations");
+    int rc = check_row(h, row);
+    if (rc) return rc;
+    rc = ensure_forces(h, 1);
+    if (rc) return rc;
+    rc = launch_step(h, kStreamOnly, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, row, 0, false);
+    if (rc) return rc;
+    h->other_has_g = true;
+    h->force_n = 1;
+    return LBM_OK;
+}
+
+int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
+{
+    CHECK_H(h);
+    if (!out || first < 0 || n < 0 || first + n > h->force_n) return fail(LBM_E_INVALID, "force slots [%lld, %lld) not available (%lld written)", (long long)first, (long long)(first + n), (long long)h->force_n);
+    const int nobs = std::max(h->n_obs, 1);
+    if (n == 0) return LBM_OK;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_forces_now(lbm_t *h, double *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(LBM_E_INVALID, "out is NULL");
+    if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_forces_now needs post-collision populations");
+    const int nobs = std::max(h->n_obs, 1);
+    if (h->n_obs == 0) { out[0] = out[1] = 0.0; return LBM_OK; }
+    // uses a private slot past the step slots
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, (size_t)nobs * 2 * sizeof(double)));
+    int rc = LBM_OK;
+    {
+        const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+        dim3 grid(h->n_link_blocks), block(kBlock);
+        if (h->cfg.dtype == LBM_F64) {
+            StepParams<double> p; LinkParams lp;
+            fill_params<double>(h, p, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, 0, 0);
+            p.walls = nullptr; lp.forces = d_out;
+            if (strict) force_kernel<double, true><<<grid, block, 0, h->stream>>>(p, lp);
+            else force_kernel<double, false><<<grid, block, 0, h->stream>>>(p, lp);
+        } else {
+            StepParams<float> p; LinkParams lp;
+            fill_params<float>(h, p, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, 0, 0);
+            p.walls = nullptr; lp.forces = d_out;
+            if (strict) force_kernel<float, true><<<grid, block, 0, h->stream>>>(p, lp);
+            else force_kernel<float, false><<<grid, block, 0, h->stream>>>(p, lp);
+        }
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "lbm_forces_now: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+int lbm_get_populations(lbm_t *h, int32_t which, void *host)
+{
+    CHECK_H(h);
+    if (!host) return fail(LBM_E_INVALID, "host is NULL");
+    int src;
+    if (which == LBM_POP_POST_COLLISION) {
+        if (h->kind != kHaveF) return fail(LBM_E_STATE, "no post-collision populations yet");
+        src = h->cur;
+    } else if (which == LBM_POP_STREAMED) {
+        if (h->kind == kHaveG) src = h->cur;
+        else if (h->kind == kHaveF && h->other_has_g) src = h->cur ^ 1;
+        else return fail(LBM_E_STATE, "streamed populations not materialised: call lbm_apply_bc first");
+    } else return fail(LBM_E_INVALID, "bad `which`");
+    return copy_field_d2h(h, elem_ptr(h, src, 0), h->lay.plane, host, 9);
+}
+
+int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host)
+{
+    CHECK_H(h);
+    if (!h->macro_valid || !h->rho) return fail(LBM_E_STATE, "no macroscopic fields stored: run lbm_step with LBM_STEP_MACRO_LAST");
+    const int64_t cells = h->cfg.nxl * h->lay.pitch;
+    int rc = LBM_OK;
+    if (rho_host) rc = copy_field_d2h(h, h->rho, cells, rho_host, 1);
+    if (!rc && u_host) rc = copy_field_d2h(h, h->u, cells, u_host, 2);
+    return rc;
+}
+
+int64_t lbm_launch_count(const lbm_t *h) { return h ? h->launches : 0; }
+
+int lbm_last_step_ms(lbm_t *h, float *ms)
+{
+    CHECK_H(h);
+    if (!ms) return fail(LBM_E_INVALID, "ms is NULL");
+    if (!h->ev_valid) return fail(LBM_E_STATE, "no lbm_step call yet");
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return LBM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+"""Drop-in replacement of the reference's ``lattice`` class on the B200 path.
+
+The reference's seam between host logic and kernels is the ``lattice`` object
+(/root/reference/lbm/src/core/lattice.py:15-286): ``run.py`` and the apps call
+its methods and read/write its array attributes, and every compute method
+forwards to one Numba kernel of ``nb.py``.  This class keeps that surface --
+same method names, same attributes, same argument meaning -- and forwards to
+the C ABI of ``include/lbm_b200.h`` through ctypes.  PyTorch is used for the two
+population buffers and the stream handle only.
+
+How the per-phase calls of the reference driver loop (run.py:24-54) map onto the
+fused update of the library:
+
+  macro()               launches ONE fused update: stream + (I)BB + Zou-He of the
+                        previous iteration (as recorded by the set_bc calls) followed
+                        by macro / equilibrium / TRT collision of this iteration.  The
+                        very first macro() after ``lattice.g = ...`` is collide-only.
+  equilibrium()         no-op after macro() (already done inside the update); before
+                        any populations exist (apps' initialize()) it evaluates
+                        nb_equilibrium on the host-side rho/u through lbm_equilibrium.
+  collision_stream()    no-op marker: opens the boundary-condition recording window.
+  zou_he_*(), bounce_back_obstacle()
+                        record which boundary treatment runs and SNAPSHOT the wall
+                        profile arrays at call time (the next set_inlets overwrites
+                        them before the next macro(), run.py:30-33).
+  drag_lift()           momentum-exchange sums of the current post-collision array
+                        (nb_drag_lift only needs g_up and IBB(g_up), nb.py:64 / 98-104).
+  .u / .rho / .g / .g_up / .g_eq
+                        host mirrors with the reference's semantics, materialised on
+                        demand.
+
+There is no CPU fallback; without the CUDA library or a GPU the constructor raises.
+"""
+import ctypes
+import math
+import os
+from datetime import datetime
+
+import numpy as np
+
+from . import _capi as C
+
+_REQUIRED_BCS = ("bottom", "left", "top", "right", "bl", "tl", "tr", "br")
+
+
+class lattice:
+    def __init__(self, app, dtype=None, arith=None, device=None, make_dirs=None):
+        # --- parameters, same defaults and hasattr ladder as lattice.py:18-78 -------------
+        defaults = dict(name="lattice", x_min=0.0, x_max=1.0, y_min=0.0, y_max=1.0, nx=100, ny=100,
+                        tau_lbm=1.0, dx=1.0, dt=1.0, dpi=100, u_lbm=0.03, L_lbm=100, nu_lbm=0.01,
+                        Re_lbm=100.0, rho_lbm=1.0, IBB=False, stop="it", t_max=1.0, it_max=1000,
+                        obs_cv_ct=1.0e-1, obs_cv_nb=500)
+        for k, v in defaults.items():
+            setattr(self, k, getattr(app, k, v))
+        self.Cx = getattr(app, "Cx", self.dx)
+        self.Ct = getattr(app, "Ct", self.dt)
+        self.Cr = getattr(app, "Ct", 1.0) if hasattr(app, "Cr") else 1.0   # sic, lattice.py:63
+        self.Cn = getattr(app, "Cn", self.Cx ** 2 / self.Ct)
+        self.Cu = getattr(app, "Cu", self.Cx / self.Ct)
+        self.Cf = getattr(app, "Cf", self.Cr * self.Cx ** 2 / self.Ct)
+        # --- B200 options: keyword, else attribute on the app, else default ----------------
+        self.dtype = dtype or getattr(app, "lbm_dtype", "f64")
+        self.arith = arith or getattr(app, "lbm_arith", "fused")
+        self.device = device if device is not None else getattr(app, "lbm_device", 0)
+        if self.dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
+        if self.arith not in ("fused", "strict"):
+            raise ValueError("arith must be 'fused' or 'strict'")
+        self._np = np.float64 if self.dtype == "f64" else np.float32
+        # --- output directories (lattice.py:80-91) -----------------------------------------
+        if make_dirs is None:
+            make_dirs = getattr(app, "lbm_make_dirs", True)
+        stamp = datetime.now().strftime("%Y-%m-%d_%H_%M_%S")
+        self.results_dir = "./results/"
+        self.output_dir = self.results_dir + stamp + "/"
+        self.png_dir = self.output_dir + "./png/"
+        if make_dirs:
+            os.makedirs(self.png_dir, exist_ok=True)
+        self._set_default_lbm()
+        self._open_device()
+
+    # ------------------------------------------------------------------------------------
+    def _set_default_lbm(self):
+        """Constants and host arrays of lattice.py:117-174."""
+        self.output_it = 0
+        self.lx, self.ly, self.q = self.nx - 1, self.ny - 1, 9
+        self.Cs = 1.0 / math.sqrt(3.0)
+        self.tau_p_lbm = self.tau_lbm
+        self.lambda_trt = 1.0 / 4.0
+        self.tau_m_lbm = self.lambda_trt / (self.tau_p_lbm - 0.5) + 0.5
+        self.om_p_lbm = 1.0 / self.tau_p_lbm
+        self.om_m_lbm = 1.0 / self.tau_m_lbm
+        self.om_lbm = 1.0 / self.tau_lbm
+        self.c = np.array([[0, 0], [1, 0], [-1, 0], [0, 1], [0, -1], [1, 1], [-1, -1], [-1, 1], [1, -1]])
+        self.w = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
+        self.ns = np.array([0, 2, 1, 4, 3, 6, 5, 8, 7])
+        nx, ny = self.nx, self.ny
+        self.u_left = np.zeros((2, ny))
+        self.u_right = np.zeros((2, ny))
+        self.u_top = np.zeros((2, nx))
+        self.u_bot = np.zeros((2, nx))
+        self.rho_right = np.zeros(ny)
+        self.lattice = np.zeros((nx, ny))
+        self._rho_host = np.ones((nx, ny))
+        self._u_host = np.zeros((2, nx, ny))
+        self._g_eq_host = None
+
+    def _open_device(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise C.LbmError(-2, "no CUDA device: lbm_b200 has no CPU fallback")
+        L = C.lib()
+        self._L = L
+        self._torch = torch
+        cfg = C.LbmCfg(nx=self.nx, ny=self.ny, x0=0, nxl=self.nx, om_p=self.om_p_lbm,
+                       om_m=self.om_m_lbm, dtype=C.LBM_F64 if self.dtype == "f64" else C.LBM_F32,
+                       arith=C.LBM_ARITH_STRICT if self.arith == "strict" else C.LBM_ARITH_FUSED,
+                       right_wall=C.LBM_RIGHT_VELOCITY, device=self.device)
+        self._cfg = cfg
+        self._h = None
+        self._right_wall = None         # decided by the first recorded right-wall call
+        self._state = "fresh"           # fresh | g | macro_done | streamed
+        self._bcs = set()
+        self._obstacles = []            # obstacles recorded by bounce_back_obstacle, in call order
+        self._links_key = None
+        self._row = np.zeros(5 * self.ny + 4 * self.nx)
+        self._row_dev = None            # copy of the row that is on the device
+        self._cache = {}
+        self.updates = 0                # fused updates executed
+
+    def _create(self, right_wall):
+        torch = self._torch
+        self._cfg.right_wall = right_wall
+        h = C.c_vp()
+        C.check(self._L.lbm_create(ctypes.byref(self._cfg), ctypes.byref(h)))
+        self._h = h
+        self._right_wall = right_wall
+        lay = C.LbmLayout()
+        C.check(self._L.lbm_get_layout(h, ctypes.byref(lay)))
+        self.layout = lay
+        tdt = torch.float64 if self.dtype == "f64" else torch.float32
+        dev = torch.device("cuda", self.device)
+        self._buf = [torch.empty(lay.elems, dtype=tdt, device=dev) for _ in range(2)]
+        C.check(self._L.lbm_set_stream(h, C.c_vp(torch.cuda.current_stream(dev).cuda_stream)))
+        C.check(self._L.lbm_bind_state(h, C.c_vp(self._buf[0].data_ptr()), C.c_vp(self._buf[1].data_ptr()),
+                                       lay.elems * lay.elem_size))
+
+    def _handle(self):
+        if self._h is None:
+            self._create(C.LBM_RIGHT_VELOCITY)
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.lbm_destroy(self._h)
+            self._h = None
+            self._buf = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------
+    # array attributes
+    # ------------------------------------------------------------------------------------
+    def _ptr(self, a):
+        return C.c_vp(a.ctypes.data)
+
+    def _apply_bc(self):
+        """Materialise stream + recorded BCs of the current post-collision array (other buffer)."""
+        if "bc" in self._cache:
+            return
+        self._macro_arrays(walls=False)      # keep the pure macro() fields before walls overwrite them
+        self._need_all_bcs()
+        self._push_walls()
+        self._push_links()
+        C.check(self._L.lbm_apply_bc(self._handle(), 0))
+        self._cache["bc"] = True
+
+    @property
+    def g(self):
+        if self._state == "fresh":
+            raise AttributeError("lattice.g has not been set yet")
+        if "g" not in self._cache:
+            h = self._handle()
+            if self._state == "streamed":
+                self._apply_bc()
+            elif self._state == "macro_done":
+                raise C.LbmError(-3, "lattice.g between macro() and collision_stream() is not kept "
+                                     "on the fused path (the update has already collided it)")
+            out = np.empty((9, self.nx, self.ny), dtype=self._np)
+            C.check(self._L.lbm_get_populations(h, C.LBM_POP_STREAMED, self._ptr(out)))
+            self._cache["g"] = out
+        return self._cache["g"]
+
+    @g.setter
+    def g(self, value):
+        arr = np.ascontiguousarray(value, dtype=self._np)
+        if arr.shape != (9, self.nx, self.ny):
+            raise ValueError("g must have shape (9, nx, ny)")
+        C.check(self._L.lbm_set_populations(self._handle(), self._ptr(arr)))
+        self._state = "g"
+        self._cache = {}
+        self._bcs = set()
+
+    @property
+    def g_up(self):
+        if self._state in ("fresh", "g"):
+            return np.zeros((9, self.nx, self.ny), dtype=self._np)
+        if "g_up" not in self._cache:
+            out = np.empty((9, self.nx, self.ny), dtype=self._np)
+            C.check(self._L.lbm_get_populations(self._handle(), C.LBM_POP_POST_COLLISION, self._ptr(out)))
+            self._cache["g_up"] = out
+        return self._cache["g_up"]
+
+    @property
+    def g_eq(self):
+        if self._state in ("fresh", "g"):
+            if self._g_eq_host is None:
+                return np.zeros((9, self.nx, self.ny), dtype=self._np)
+            return self._g_eq_host
+        if "g_eq" not in self._cache:
+            rho, u = self._macro_arrays(walls=False)
+            self._cache["g_eq"] = self._equilibrium_of(rho, u)
+        return self._cache["g_eq"]
+
+    def _macro_arrays(self, walls):
+        """(rho, u) host copies; walls=True adds the Zou-He overwrites of the recorded BCs."""
+        key = "macro_w" if walls else "macro"
+        if key not in self._cache:
+            if walls:
+                self._apply_bc()
+            rho = np.empty((self.nx, self.ny), dtype=self._np)
+            u = np.empty((2, self.nx, self.ny), dtype=self._np)
+            C.check(self._L.lbm_get_macro(self._handle(), self._ptr(rho), self._ptr(u)))
+            self._cache[key] = (rho, u)
+        return self._cache[key]
+
+    def _fields(self):
+        if self._state in ("fresh", "g"):
+            return self._rho_host, self._u_host
+        # after set_bc the reference has overwritten the wall entries (nb.py:127-131 ...)
+        walls = self._state == "streamed" and len(self._bcs) > 0
+        return self._macro_arrays(walls)
+
+    @property
+    def rho(self):
+        return self._fields()[0]
+
+    @rho.setter
+    def rho(self, value):
+        if self._state in ("fresh", "g"):
+            self._rho_host = np.asarray(value, dtype=np.float64).reshape(self.nx, self.ny)
+
+    @property
+    def u(self):
+        return self._fields()[1]
+
+    @u.setter
+    def u(self, value):
+        if self._state in ("fresh", "g"):
+            self._u_host = np.asarray(value, dtype=np.float64).reshape(2, self.nx, self.ny)
+
+    # ------------------------------------------------------------------------------------
+    # phases of the driver loop
+    # ------------------------------------------------------------------------------------
+    def _equilibrium_of(self, rho, u):
+        out = np.empty((9, self.nx, self.ny), dtype=self._np)
+        r = np.ascontiguousarray(rho, dtype=self._np)
+        v = np.ascontiguousarray(u, dtype=self._np)
+        C.check(self._L.lbm_equilibrium(self._handle(), self._ptr(r), self._ptr(v), self._ptr(out)))
+        return out
+
+    def equilibrium(self):
+        """nb_equilibrium (lattice.py:193-195).  Inside the loop it is part of macro()'s update."""
+        if self._state in ("fresh", "g"):
+            self._g_eq_host = self._equilibrium_of(self._rho_host, self._u_host)
+
+    def macro(self):
+        """lattice.macro (lattice.py:178-189) -- executes the fused update, see module docstring."""
+        h = self._handle()
+        if self._state == "macro_done":
+            return                      # macro() twice without collision_stream(): same fields
+        if self._state == "fresh":
+            raise C.LbmError(-3, "macro() before lattice.g was set")
+        if self._state == "streamed":
+            self._need_all_bcs()
+            self._push_walls()
+            self._push_links()
+        C.check(self._L.lbm_step(h, 1, 0, 0, C.LBM_STEP_MACRO_LAST))
+        self.updates += 1
+        self._state = "macro_done"
+        self._cache = {}
+
+    def collision_stream(self):
+        """nb_col_str (lattice.py:199-205): already executed by macro(); opens the BC window."""
+        if self._state != "macro_done":
+            raise C.LbmError(-3, "collision_stream() must follow macro()")
+        self._state = "streamed"
+        self._bcs = set()
+        self._obstacles = []
+        self._cache = {}
+
+    def _need_all_bcs(self):
+        missing = [b for b in _REQUIRED_BCS if b not in self._bcs]
+        if missing:
+            raise C.LbmError(-5, "the fused update needs all four walls and four corners to be "
+                                 "applied every iteration (missing: %s)" % ", ".join(missing))
+
+    def _record(self, name):
+        if self._state != "streamed":
+            raise C.LbmError(-3, "boundary conditions must follow collision_stream()")
+        self._bcs.add(name)
+        self._cache = {}
+
+    def zou_he_left_wall_velocity(self):
+        self._record("left")
+        self._row[0:2 * self.ny] = self.u_left.reshape(-1)
+
+    def zou_he_right_wall_velocity(self):
+        self._record("right")
+        self._switch_right(C.LBM_RIGHT_VELOCITY)
+        self._row[2 * self.ny:4 * self.ny] = self.u_right.reshape(-1)
+
+    def zou_he_right_wall_pressure(self):
+        self._record("right")
+        self._switch_right(C.LBM_RIGHT_PRESSURE)
+        self._row[2 * self.ny:4 * self.ny] = self.u_right.reshape(-1)
+        self._row[4 * self.ny + 4 * self.nx:] = self.rho_right
+
+    def zou_he_top_wall_velocity(self):
+        self._record("top")
+        self._row[4 * self.ny:4 * self.ny + 2 * self.nx] = self.u_top.reshape(-1)
+
+    def zou_he_bottom_wall_velocity(self):
+        self._record("bottom")
+        self._row[4 * self.ny + 2 * self.nx:4 * self.ny + 4 * self.nx] = self.u_bot.reshape(-1)
+
+    def zou_he_bottom_left_corner(self):
+        self._record("bl")
+
+    def zou_he_top_left_corner(self):
+        self._record("tl")
+
+    def zou_he_top_right_corner(self):
+        self._record("tr")
+
+    def zou_he_bottom_right_corner(self):
+        self._record("br")
+
+    def _switch_right(self, kind):
+        """Velocity or pressure variant on the right side: a per-update parameter of the library."""
+        if self._right_wall != kind:
+            C.check(self._L.lbm_set_right_wall(self._handle(), kind))
+            self._right_wall = kind
+            self._cache = {}
+
+    def bounce_back_obstacle(self, obstacle):
+        """nb_bounce_back_obstacle (lattice.py:218-222): recorded, executed by the next update."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "boundary conditions must follow collision_stream()")
+        self._obstacles.append(obstacle)
+        self._cache = {}
+
+    def _push_walls(self):
+        if self._row_dev is None or not np.array_equal(self._row, self._row_dev):
+            C.check(self._L.lbm_set_walls(self._handle(), 1, self._ptr(self._row)))
+            C.check(self._L.lbm_sync(self._handle()))
+            self._row_dev = self._row.copy()
+
+    def _push_links(self):
+        obs = self._obstacles
+        key = (bool(self.IBB),) + tuple((id(o), id(o.boundary), len(o.boundary)) for o in obs)
+        if key == self._links_key:
+            return
+        h = self._handle()
+        if not obs:
+            C.check(self._L.lbm_set_links(h, 0, None, None, None, 0))
+        else:
+            off = np.cumsum([0] + [len(o.boundary) for o in obs]).astype(np.int64)
+            ijq = np.ascontiguousarray(np.concatenate([np.asarray(o.boundary).reshape(-1, 3) for o in obs]),
+                                       dtype=np.int64)
+            if self.IBB:
+                ibb = np.ascontiguousarray(np.concatenate([np.asarray(o.ibb).reshape(-1) for o in obs]),
+                                           dtype=np.float64)
+                C.check(self._L.lbm_set_links(h, len(obs), self._ptr(off), self._ptr(ijq), self._ptr(ibb), 1))
+            else:
+                C.check(self._L.lbm_set_links(h, len(obs), self._ptr(off), self._ptr(ijq), None, 0))
+        self._links_key = key
+        self._link_obstacles = list(obs)
+
+    def drag_lift(self, obs, R_ref, U_ref, L_ref):
+        """nb_drag_lift (lattice.py:209-214, nb.py:49-73)."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "drag_lift() must follow set_bc")
+        if not any(o is obs for o in self._obstacles):
+            # the reference can evaluate any obstacle; here it must have been bounced back
+            self._obstacles.append(obs)
+        self._push_links()
+        k = [i for i, o in enumerate(self._link_obstacles) if o is obs][0]
+        out = np.zeros(2 * len(self._link_obstacles))
+        C.check(self._L.lbm_forces_now(self._handle(), self._ptr(out)))
+        fx, fy = float(out[2 * k]), float(out[2 * k + 1])
+        Cx = -2.0 * fx / (R_ref * L_ref * U_ref ** 2)
+        Cy = -2.0 * fy / (R_ref * L_ref * U_ref ** 2)
+        return Cx, Cy
+
+    # ------------------------------------------------------------------------------------
+    # host helpers of the reference class that the apps call
+    # ------------------------------------------------------------------------------------
+    def get_coords(self, i, j):
+        """lattice.py:379-387."""
+        dx = (self.x_max - self.x_min) / (self.nx - 1)
+        dy = (self.y_max - self.y_min) / (self.ny - 1)
+        return [self.x_min + i * dx, self.y_min + j * dy]
+
+    def generate_image(self, obstacles):
+        """Output writer of the reference (lattice.py:418-436): out of scope, see DESIGN.md."""
+        return None

@@ -1,0 +1,166 @@
+"""Thin object wrapper of one C-ABI handle (include/lbm_b200.h) for batched runs, bench.py and
+the slab driver.  Device buffers come from PyTorch; nothing here touches the CPU oracle."""
+import ctypes
+
+import numpy as np
+
+from . import _capi as C
+
+
+class Solver:
+    def __init__(self, nx, ny, tau=None, om_p=None, om_m=None, dtype="f64", arith="fused",
+                 right_wall="velocity", device=0, x0=0, nxl=None, stream=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise C.LbmError(-2, "no CUDA device: lbm_b200 has no CPU fallback")
+        self._torch = torch
+        self._L = C.lib()
+        if om_p is None:
+            # TRT rates from tau, lattice.py:127-131
+            tau_m = 0.25 / (tau - 0.5) + 0.5
+            om_p, om_m = 1.0 / tau, 1.0 / tau_m
+        self.nx, self.ny, self.x0 = int(nx), int(ny), int(x0)
+        self.nxl = int(nx if nxl is None else nxl)
+        self.dtype = dtype
+        self.np_dtype = np.float64 if dtype == "f64" else np.float32
+        cfg = C.LbmCfg(nx=self.nx, ny=self.ny, x0=self.x0, nxl=self.nxl, om_p=om_p, om_m=om_m,
+                       dtype=C.LBM_F64 if dtype == "f64" else C.LBM_F32,
+                       arith=C.LBM_ARITH_STRICT if arith == "strict" else C.LBM_ARITH_FUSED,
+                       right_wall=C.LBM_RIGHT_PRESSURE if right_wall == "pressure" else C.LBM_RIGHT_VELOCITY,
+                       device=device)
+        h = C.c_vp()
+        C.check(self._L.lbm_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self.layout = C.LbmLayout()
+        C.check(self._L.lbm_get_layout(h, ctypes.byref(self.layout)))
+        lay = self.layout
+        self.device = torch.device("cuda", device)
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        self.buffers = [torch.empty(lay.elems, dtype=tdt, device=self.device) for _ in range(2)]
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.stream = s
+        C.check(self._L.lbm_set_stream(h, C.c_vp(s.cuda_stream)))
+        C.check(self._L.lbm_bind_state(h, C.c_vp(self.buffers[0].data_ptr()),
+                                       C.c_vp(self.buffers[1].data_ptr()), lay.elems * lay.elem_size))
+        self.row_len = int(self._L.lbm_wall_row_len(h))
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.lbm_destroy(self._h)
+            self._h = None
+            self.buffers = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ------------------------------------------------------------------------
+    @staticmethod
+    def _p(a):
+        return C.c_vp(a.ctypes.data)
+
+    def set_populations(self, g):
+        g = np.ascontiguousarray(g, dtype=self.np_dtype)
+        assert g.shape == (9, self.nxl, self.ny)
+        C.check(self._L.lbm_set_populations(self._h, self._p(g)))
+
+    def init_equilibrium(self, rho=1.0, ux=0.0, uy=0.0):
+        C.check(self._L.lbm_init_equilibrium(self._h, rho, ux, uy))
+
+    def set_links(self, obstacles, use_ibb=True):
+        if not obstacles:
+            C.check(self._L.lbm_set_links(self._h, 0, None, None, None, 0))
+            return
+        off = np.cumsum([0] + [len(o.boundary) for o in obstacles]).astype(np.int64)
+        ijq = np.ascontiguousarray(np.concatenate([np.asarray(o.boundary).reshape(-1, 3) for o in obstacles]), dtype=np.int64)
+        ibb = np.ascontiguousarray(np.concatenate([np.asarray(o.ibb).reshape(-1) for o in obstacles]), dtype=np.float64)
+        self.n_obs = len(obstacles)
+        C.check(self._L.lbm_set_links(self._h, len(obstacles), self._p(off), self._p(ijq),
+                                      self._p(ibb) if use_ibb else None, 1 if use_ibb else 0))
+
+    def wall_row(self, u_left=None, u_right=None, u_top=None, u_bot=None, rho_right=None):
+        """Pack one wall row: [u_left(2,ny) | u_right(2,ny) | u_top(2,nx) | u_bot(2,nx) | rho_right(ny)]."""
+        nx, ny = self.nx, self.ny
+        row = np.zeros(self.row_len)
+        for arr, a, n in ((u_left, 0, 2 * ny), (u_right, 2 * ny, 2 * ny), (u_top, 4 * ny, 2 * nx),
+                          (u_bot, 4 * ny + 2 * nx, 2 * nx), (rho_right, 4 * ny + 4 * nx, ny)):
+            if arr is not None:
+                row[a:a + n] = np.asarray(arr, dtype=np.float64).reshape(-1)
+        return row
+
+    def set_walls(self, rows):
+        """rows: (n_rows, row_len) float64 array (numpy) or pinned torch tensor."""
+        if hasattr(rows, "data_ptr"):
+            n = rows.shape[0] if rows.dim() == 2 else 1
+            C.check(self._L.lbm_set_walls(self._h, n, C.c_vp(rows.data_ptr())))
+            self._walls_keepalive = rows
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self.row_len)
+            C.check(self._L.lbm_set_walls(self._h, rows.shape[0], self._p(rows)))
+            self._walls_keepalive = rows
+
+    def set_right_wall(self, kind):
+        C.check(self._L.lbm_set_right_wall(self._h, C.LBM_RIGHT_PRESSURE if kind == "pressure" else C.LBM_RIGHT_VELOCITY))
+
+    # -- stepping ---------------------------------------------------------------------
+    def step(self, n=1, first_row=0, row_stride=0, macro_last=False):
+        C.check(self._L.lbm_step(self._h, n, first_row, row_stride, C.LBM_STEP_MACRO_LAST if macro_last else 0))
+
+    def step_columns(self, xa, xb, row=0, slot=0):
+        C.check(self._L.lbm_step_columns(self._h, xa, xb, row, slot, 0))
+
+    def flip(self):
+        C.check(self._L.lbm_flip(self._h))
+
+    def apply_bc(self, row=0):
+        C.check(self._L.lbm_apply_bc(self._h, row))
+
+    def sync(self):
+        C.check(self._L.lbm_sync(self._h))
+
+    def last_step_ms(self):
+        ms = ctypes.c_float()
+        C.check(self._L.lbm_last_step_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launches(self):
+        return int(self._L.lbm_launch_count(self._h))
+
+    # -- results ----------------------------------------------------------------------
+    def forces(self, first, n):
+        nobs = max(getattr(self, "n_obs", 0), 1)
+        out = np.zeros((n, nobs, 2))
+        C.check(self._L.lbm_get_forces(self._h, first, n, self._p(out)))
+        return out
+
+    def forces_now(self):
+        nobs = max(getattr(self, "n_obs", 0), 1)
+        out = np.zeros((nobs, 2))
+        C.check(self._L.lbm_forces_now(self._h, self._p(out)))
+        return out
+
+    def populations(self, which="post_collision"):
+        out = np.empty((9, self.nxl, self.ny), dtype=self.np_dtype)
+        w = C.LBM_POP_POST_COLLISION if which == "post_collision" else C.LBM_POP_STREAMED
+        C.check(self._L.lbm_get_populations(self._h, w, self._p(out)))
+        return out
+
+    def macro(self):
+        rho = np.empty((self.nxl, self.ny), dtype=self.np_dtype)
+        u = np.empty((2, self.nxl, self.ny), dtype=self.np_dtype)
+        C.check(self._L.lbm_get_macro(self._h, self._p(rho), self._p(u)))
+        return rho, u
+
+    def current_view(self):
+        """Torch view [9, nxl+2, pitch] of the buffer holding the current populations (halo columns
+        at index 0 and nxl+1)."""
+        cur, oth = C.c_vp(), C.c_vp()
+        C.check(self._L.lbm_state_ptrs(self._h, ctypes.byref(cur), ctypes.byref(oth)))
+        buf = self.buffers[0] if cur.value == self.buffers[0].data_ptr() else self.buffers[1]
+        lay = self.layout
+        start = lay.origin - lay.pitch
+        return buf[start:start + 9 * lay.plane].view(9, self.nxl + 2, lay.pitch)

@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI, behind the drop-in `lattice` class)
+against the CPU oracle on identical inputs, and against the committed golden vectors that
+were produced by the reference itself.
+
+Tolerances: STRICT arithmetic is bit-identical to the oracle (== on every array);
+FUSED (FMA contraction, the production mode) is within 1e-12 of max|ref| in f64 and 1e-5 in
+f32 (BASELINE.json north_star); drag/lift coefficients within 1e-6 absolute."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from lbm_b200 import cases
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def gpu_lattice(case, **kw):
+    from lbm_b200.lattice import lattice
+    return lattice(case, make_dirs=False, **kw)
+
+
+def make_case(name):
+    if name == "cavity32":
+        return cases.Cavity(L_lbm=32, sigma=20)
+    if name == "turek30":
+        z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+        return cases.Turek(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])])
+    if name == "poiseuille20":
+        return cases.Poiseuille(L_lbm=20, sigma=10)
+    if name == "cavity200":
+        return cases.Cavity(L_lbm=200)
+    if name == "turek100":
+        return cases.Turek(L_lbm=100, Re_lbm=20.0, sigma=60)
+    if name == "turek200":
+        return cases.Turek(L_lbm=200, Re_lbm=100.0, sigma=60)
+    if name == "array":
+        return cases.Array(sigma=40)
+    raise KeyError(name)
+
+
+def run_both(name, n, **kw):
+    c_gpu, c_cpu = make_case(name), make_case(name)
+    lat_g = gpu_lattice(c_gpu, **kw)
+    orc.run_loop(lat_g, c_gpu, n_iters=n)
+    lat_o = orc.OracleLattice(c_cpu)
+    orc.run_loop(lat_o, c_cpu, n_iters=n)
+    return lat_g, c_gpu, lat_o, c_cpu
+
+
+@pytest.mark.parametrize("name,n", [("cavity32", 150), ("turek30", 120), ("poiseuille20", 100)])
+def test_strict_is_bit_identical_to_oracle(name, n):
+    lat_g, c_gpu, lat_o, c_cpu = run_both(name, n, arith="strict")
+    for k in ("g_up", "g", "rho", "u"):
+        a, b = getattr(lat_g, k), getattr(lat_o, k)
+        assert a.dtype == np.float64 and np.array_equal(a, b), "%s differs (max %g)" % (k, np.max(np.abs(a - b)))
+    if c_gpu.forces:
+        f, fo = np.array(c_gpu.forces), np.array(c_cpu.forces)
+        assert np.max(np.abs(f - fo)) <= 1e-13 * np.max(np.abs(fo))   # summation order only
+
+
+@pytest.mark.parametrize("name", ["cavity32", "turek30", "poiseuille20"])
+def test_fused_matches_reference_golden_run(name):
+    """Free-running GPU run against arrays stored from a run of the reference itself."""
+    z = np.load(os.path.join(GOLDEN, "run_%s.npz" % name))
+    case = make_case(name)
+    lat = gpu_lattice(case)
+    orc.run_loop(lat, case, n_iters=int(z["n_iters"]))
+    for k in ("g", "g_up", "rho", "u"):
+        assert rel(getattr(lat, k), z[k]) < 1e-12, k
+    if name == "turek30":
+        assert np.max(np.abs(np.array(case.forces) - z["forces"])) < 1e-9
+
+
+@pytest.mark.parametrize("name,n", [("cavity200", 600), ("turek100", 500), ("turek200", 300), ("array", 200)])
+def test_baseline_configs_bounded_horizon(name, n):
+    """BASELINE configs 1-4 at their real sizes over a bounded horizon (the flows are chaotic
+    amplifiers of rounding beyond it)."""
+    lat_g, c_gpu, lat_o, c_cpu = run_both(name, n)
+    for k in ("g", "g_up", "rho", "u"):
+        assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 1e-12, k
+    if c_gpu.forces:
+        f, fo = np.array(c_gpu.forces), np.array(c_cpu.forces)
+        assert f.shape == fo.shape == (n, 2)
+        assert np.max(np.abs(f - fo)) < 1e-6
+
+
+@pytest.mark.parametrize("name,n", [("cavity32", 150), ("turek30", 120)])
+def test_f32_variant(name, n):
+    lat_g, c_gpu, lat_o, c_cpu = run_both(name, n, dtype="f32")
+    assert lat_g.g_up.dtype == np.float32
+    for k in ("g", "g_up", "rho", "u"):
+        assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 1e-5, k
+
+
+def test_equilibrium_entry_point_matches_golden():
+    z = np.load(os.path.join(GOLDEN, "phases.npz"))
+
+    class P:
+        nx, ny, tau_lbm = int(z["nx"]), int(z["ny"]), 0.62
+    lat = gpu_lattice(P(), arith="strict")
+    lat.rho = z["rho0"].copy()
+    lat.u = z["u0"].copy()
+    lat.equilibrium()
+    assert rel(lat.g_eq, z["g_eq"]) < 5e-16
+
+
+def test_single_update_against_golden_phases():
+    """One fused update from the golden g_in: collide (nb_col_str) then stream + BCs; compares the
+    post-collision array and the streamed array with the reference's nb_col_str outputs away
+    from the walls."""
+    z = np.load(os.path.join(GOLDEN, "phases.npz"))
+
+    class P:
+        nx, ny, tau_lbm = int(z["nx"]), int(z["ny"]), 0.62
+    case = cases.Cavity(L_lbm=32)
+    lat = gpu_lattice(P())
+    lat.g = z["g_in"].copy()
+    lat.macro()
+    assert rel(lat.rho, z["macro_rho"]) < 1e-15 and rel(lat.u, z["macro_u"]) < 1e-14
+    assert rel(lat.g_up, z["cs_g_up"]) < 1e-15
+    lat.equilibrium()
+    lat.collision_stream()
+    for k in ("u_left", "u_right", "u_top", "u_bot", "rho_right"):
+        getattr(lat, k)[:] = z[k]
+    case.set_bc(lat)
+    g = lat.g
+    inner = (slice(None), slice(1, -1), slice(1, -1))
+    assert rel(g[inner], z["cs_g"][inner]) < 1e-15
+    # left / right / top / bottom walls away from the corners against the per-wall goldens
+    assert rel(g[:, 0, 1:-1], z["zh_left_g"][:, 0, 1:-1]) < 1e-15
+    assert rel(g[:, -1, 1:-1], z["zh_right_g"][:, -1, 1:-1]) < 1e-15
+    assert rel(g[:, 1:-1, -1], z["zh_top_g"][:, 1:-1, -1]) < 1e-15
+    assert rel(g[:, 1:-1, 0], z["zh_bottom_g"][:, 1:-1, 0]) < 1e-15
+    for (i, j) in ((0, 0), (0, -1), (-1, -1), (-1, 0)):
+        assert rel(g[:, i, j], z["corner_g"][:, i, j]) < 1e-15
+    # pressure variant on the right
+    lat2 = gpu_lattice(P())
+    lat2.g = z["g_in"].copy()
+    lat2.macro(); lat2.equilibrium(); lat2.collision_stream()
+    for k in ("u_left", "u_right", "u_top", "u_bot", "rho_right"):
+        getattr(lat2, k)[:] = z[k]
+    cases.Poiseuille(L_lbm=20).set_bc(lat2)
+    assert rel(lat2.g[:, -1, 1:-1], z["zh_rightp_g"][:, -1, 1:-1]) < 1e-15
+    assert rel(lat2.u[:, -1, 1:-1], z["zh_rightp_u"][:, -1, 1:-1]) < 1e-13
+
+
+def test_bounce_back_variants_against_golden():
+    z = np.load(os.path.join(GOLDEN, "phases.npz"))
+
+    class P:
+        nx, ny, tau_lbm = int(z["nx"]), int(z["ny"]), 0.62
+    obs = cases.Obstacle(z["bb_boundary"], z["bb_ibb"])
+    for ibb, key in ((True, "bb_ibb_g"), (False, "bb_plain_g")):
+        p = P()
+        p.IBB = ibb
+        lat = gpu_lattice(p)
+        lat.g = z["g_in"].copy()
+        lat.macro(); lat.equilibrium(); lat.collision_stream()
+        case = cases.Cavity(L_lbm=32)
+        case.obstacles = [obs]
+        case.set_bc(lat)
+        inner = (slice(None), slice(1, -1), slice(1, -1))
+        assert rel(lat.g[inner], z[key][inner]) < 1e-15
+        if ibb:
+            cx, cy = lat.drag_lift(obs, 1.0, 0.03, 7.0)
+            assert abs(cx - z["drag_lift"][0]) < 1e-11 * abs(z["drag_lift"][0])
+            assert abs(cy - z["drag_lift"][1]) < 1e-11 * abs(z["drag_lift"][1])
+
+
+def test_rejects_out_of_range_links():
+    """The reference wraps negative link indices silently; the library refuses."""
+    from lbm_b200._capi import LbmError
+    case = cases.Cavity(L_lbm=32)
+    bad = cases.Obstacle(np.array([[5, -1, 3]]), np.array([0.3]))
+    lat = gpu_lattice(case)
+    case.initialize(lat)
+    lat.macro(); lat.equilibrium(); lat.collision_stream()
+    case.obstacles = [bad]
+    case.set_bc(lat)
+    with pytest.raises(LbmError):
+        lat.macro()
+
+
+def test_large_grid_against_oracle():
+    """2048 x 1024 cavity-type grid, 12 updates: exercises multi-tile indexing and 64-bit offsets."""
+    case_g, case_o = cases.Cavity(L_lbm=1024, sigma=5), cases.Cavity(L_lbm=1024, sigma=5)
+    for c in (case_g, case_o):
+        c.x_max = 2.0
+        c.nx = 2048
+    lat_g = gpu_lattice(case_g)
+    lat_o = orc.OracleLattice(case_o)
+    orc.run_loop(lat_g, case_g, n_iters=12)
+    orc.run_loop(lat_o, case_o, n_iters=12)
+    for k in ("g", "g_up", "rho", "u"):
+        assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 1e-12, k
