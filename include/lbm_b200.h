@@ -163,6 +163,13 @@ int lbm_get_populations(lbm_t *h, int32_t which, void *host);
  * overwrites of a later lbm_apply_bc): the composite the reference leaves in lattice.rho/u. */
 int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host);
 
+/* rho, ux, uy along one lattice line of the streamed + boundary-treated current populations,
+ * i.e. what lattice.macro() (lattice.py:178-189) of the next iteration yields there; serves the
+ * centre-line readers cavity.line_fields (cavity.py:110-133) and poiseuille.compute_error
+ * (poiseuille.py:128-152) without a full-field transfer.  axis 0: column x = index (ny values),
+ * axis 1: row y = index (nxl values).  out_host: [rho | ux | uy], 3*n elements of the handle dtype. */
+int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out_host);
+
 /* Launch counter: kernels launched by this handle since creation (bench.py gpu_launches). */
 int64_t lbm_launch_count(const lbm_t *h);
 /* Device time of the updates of the last lbm_step call, from CUDA events recorded on the

@@ -267,6 +267,26 @@ force_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Li
     link_block<T, STRICT, kFused, true>(p, lp, blockIdx.x, kBlock);
 }
 
+// Macroscopic fields of the streamed + boundary-treated populations along one lattice line
+// (what lattice.macro() of the next iteration computes there): axis 0 -> column x = index
+// (ny cells), axis 1 -> row y = index (nxl cells).  out = [rho | ux | uy], each n long.
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n, T *out)
+{
+    using A = Ar<T, STRICT>;
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n) return;
+    const int x = axis == 0 ? index : k, y = axis == 0 ? k : index;
+    T G[9], r, ux, uy;
+    pull(p, x, y, G);
+    apply_walls<A, T>(p, x, y, G, r, ux, uy);
+    macro<A, T>(G, r, ux, uy);
+    out[k] = r;
+    out[n + k] = ux;
+    out[2 * n + k] = uy;
+}
+
 // uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
 template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kBlock)
@@ -353,6 +373,8 @@ struct lbm_handle {
     // forces
     double *d_forces = nullptr;
     int64_t force_cap = 0, force_n = 0;
+    void *d_probe = nullptr;
+    int64_t probe_cap = 0;
     // accounting
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -563,6 +585,7 @@ int lbm_destroy(lbm_t *h)
     if (h->rho) cudaFree(h->rho);
     if (h->u) cudaFree(h->u);
     if (h->d_forces) cudaFree(h->d_forces);
+    if (h->d_probe) cudaFree(h->d_probe);
     free_links(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1008,6 +1031,43 @@ int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host)
     if (rho_host) rc = copy_field_d2h(h, h->rho, cells, rho_host, 1);
     if (!rc && u_host) rc = copy_field_d2h(h, h->u, cells, u_host, 2);
     return rc;
+}
+
+int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out_host)
+{
+    CHECK_H(h);
+    if (!out_host) return fail(LBM_E_INVALID, "out_host is NULL");
+    if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_probe_line needs post-collision populations");
+    if (h->n_obs > 0) return fail(LBM_E_UNSUPPORTED, "lbm_probe_line ignores obstacle links; not available with obstacles");
+    if (axis != 0 && axis != 1) return fail(LBM_E_INVALID, "axis must be 0 (column) or 1 (row)");
+    const int64_t n = axis == 0 ? h->cfg.ny : h->cfg.nxl;
+    const int64_t lim = axis == 0 ? h->cfg.nxl : h->cfg.ny;
+    if (index < 0 || index >= lim) return fail(LBM_E_INVALID, "line index out of range");
+    int rc = check_row(h, row);
+    if (rc) return rc;
+    if (!h->d_probe || h->probe_cap < 3 * n) {
+        if (h->d_probe) { CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->d_probe)); h->d_probe = nullptr; }
+        CUDA_TRY(cudaMalloc(&h->d_probe, (size_t)3 * n * h->esz));
+        h->probe_cap = 3 * n;
+    }
+    dim3 grid((unsigned)((n + kBlock - 1) / kBlock)), block(kBlock);
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    if (h->cfg.dtype == LBM_F64) {
+        StepParams<double> p; LinkParams lp;
+        fill_params<double>(h, p, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, row, 0);
+        if (strict) probe_kernel<double, true><<<grid, block, 0, h->stream>>>(p, axis, (int)index, (int)n, (double *)h->d_probe);
+        else probe_kernel<double, false><<<grid, block, 0, h->stream>>>(p, axis, (int)index, (int)n, (double *)h->d_probe);
+    } else {
+        StepParams<float> p; LinkParams lp;
+        fill_params<float>(h, p, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, row, 0);
+        if (strict) probe_kernel<float, true><<<grid, block, 0, h->stream>>>(p, axis, (int)index, (int)n, (float *)h->d_probe);
+        else probe_kernel<float, false><<<grid, block, 0, h->stream>>>(p, axis, (int)index, (int)n, (float *)h->d_probe);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_host, h->d_probe, (size_t)3 * n * h->esz, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
 }
 
 int64_t lbm_launch_count(const lbm_t *h) { return h ? h->launches : 0; }

@@ -155,12 +155,22 @@ class Solver:
         C.check(self._L.lbm_get_macro(self._h, self._p(rho), self._p(u)))
         return rho, u
 
-    def current_view(self):
-        """Torch view [9, nxl+2, pitch] of the buffer holding the current populations (halo columns
-        at index 0 and nxl+1)."""
+    def probe_line(self, axis, index, row=0):
+        """(rho, ux, uy) along column x=index (axis 0) or row y=index (axis 1)."""
+        n = self.ny if axis == 0 else self.nxl
+        out = np.empty((3, n), dtype=self.np_dtype)
+        C.check(self._L.lbm_probe_line(self._h, axis, index, row, self._p(out)))
+        return out
+
+    def views(self):
+        """Torch views [9, nxl+2, pitch] of (current, other) population buffers; column index = x + 1
+        (index 0 and nxl+1 are the halo columns)."""
         cur, oth = C.c_vp(), C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._h, ctypes.byref(cur), ctypes.byref(oth)))
-        buf = self.buffers[0] if cur.value == self.buffers[0].data_ptr() else self.buffers[1]
+        i = 0 if cur.value == self.buffers[0].data_ptr() else 1
         lay = self.layout
         start = lay.origin - lay.pitch
-        return buf[start:start + 9 * lay.plane].view(9, self.nxl + 2, lay.pitch)
+
+        def v(buf):
+            return buf[start:start + 9 * lay.plane].view(9, self.nxl + 2, lay.pitch)
+        return v(self.buffers[i]), v(self.buffers[i ^ 1])

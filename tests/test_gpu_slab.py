@@ -1,0 +1,31 @@
+"""GPU, >= 2 devices: slab-decomposed run == single-GPU run, bitwise."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("overlap", [1, 0])
+def test_slab_equals_single_gpu(overlap):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29611 + overlap),
+           os.path.join(ROOT, "tests", "slab_worker.py"), "515", "300", "40", str(overlap)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    out = json.loads(line)
+    assert out["ok"] and out["max_abs_diff"] == 0.0 and out["world"] == world

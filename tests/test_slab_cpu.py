@@ -1,0 +1,83 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path -- slab partition and
+the halo exchange plan -- checked by doing a pull-stream on each slab with NumPy and comparing it
+with the pull-stream of the undivided lattice."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lbm_b200 import slab  # noqa: E402
+
+CX = [0, 1, -1, 0, 0, 1, -1, -1, 1]
+CY = [0, 0, 0, 1, -1, 1, -1, 1, -1]
+
+
+def test_slab_bounds_cover_the_domain():
+    for nx, world in ((32768, 8), (1073, 4), (17, 8), (200, 3)):
+        xs = [slab.slab_bounds(nx, world, r) for r in range(world)]
+        assert xs[0][0] == 0 and xs[-1][0] + xs[-1][1] == nx
+        for (a, n), (b, _) in zip(xs[:-1], xs[1:]):
+            assert a + n == b and n >= 2
+        assert max(n for _, n in xs) - min(n for _, n in xs) <= 1
+    with pytest.raises(ValueError):
+        slab.slab_bounds(7, 4, 0)
+
+
+def _pull_interior(F):
+    """G_q(x, y) = F_q(x - cx, y - cy) for 1 <= y < ny-1 and every x whose source column exists."""
+    q, nxp, ny = F.shape
+    G = np.full_like(F, np.nan)
+    for k in range(9):
+        for x in range(nxp):
+            xs = x - CX[k]
+            if 0 <= xs < nxp:
+                G[k, x, 1:ny - 1] = F[k, xs, 1 - CY[k]:ny - 1 - CY[k]]
+    return G
+
+
+def _worker(rank, world, port, nx, ny, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    F = rng.standard_normal((9, nx, ny))                     # same on every rank
+    x0, nxl = slab.slab_bounds(nx, world, rank)
+    pitch = ny + 3                                           # padded lines, like the device layout
+    view = torch.full((9, nxl + 2, pitch), float("nan"), dtype=torch.float64)
+    view[:, 1:nxl + 1, :ny] = torch.from_numpy(F[:, x0:x0 + nxl])
+    slab.exchange_halos(view, nxl, rank, world, dist)
+    local = view.numpy()[:, :, :ny]
+    G = _pull_interior(local)[:, 1:nxl + 1]                  # owned columns
+    ref = _pull_interior(F)[:, x0:x0 + nxl]
+    ok = True
+    for x in range(nxl):
+        gx = x0 + x
+        for k in range(9):
+            if 0 <= gx - CX[k] < nx:                         # source exists in the global lattice
+                ok &= np.array_equal(G[k, x, 1:ny - 1], ref[k, x, 1:ny - 1])
+    # halo entries that no owned cell pulls from must not have been touched
+    untouched = [k for k in range(9) if k not in slab.Q_RIGHT]
+    if rank > 0:
+        ok &= bool(np.isnan(view.numpy()[untouched, 0, :ny]).all())
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nx", [(2, 11), (3, 10)])
+def test_halo_exchange_feeds_the_pull_stream(world, nx):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, nx, 9, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)) and len(out) == world
