@@ -416,6 +416,22 @@ class lattice:
         dy = (self.y_max - self.y_min) / (self.ny - 1)
         return [self.x_min + i * dx, self.y_min + j * dy]
 
+    def add_obstacle(self, obstacle):
+        """lattice.add_obstacle (lattice.py:290-375): host preprocessing, see geometry.py."""
+        from . import geometry
+        print('# Obstacle ', str(obstacle.tag))
+        area, bnd, ibb = geometry.add_obstacle(self, obstacle)
+        print('# ' + str(int(np.count_nonzero(self.lattice == obstacle.tag))) + ' locations in obstacle')
+        print('# ' + str(bnd.shape[0]) + ' locations on boundary')
+        print('# Area = ' + '{:f}'.format(area))
+        print('')
+        return area, bnd, ibb
+
+    def is_inside(self, poly, pt):
+        """lattice.is_inside (lattice.py:391-414) for one point."""
+        from . import geometry
+        return bool(geometry.inside_polygon(np.asarray(poly), np.array([pt[0]]), np.array([pt[1]]))[0])
+
     def generate_image(self, obstacles):
         """Output writer of the reference (lattice.py:418-436): out of scope, see DESIGN.md."""
         return None

@@ -86,3 +86,18 @@ def test_array_live():
     orc.run_loop(lat, case, n_iters=150)
     for k in ("g", "g_up", "rho", "u"):
         assert rel(getattr(lat, k), getattr(ref, k)) < 1e-12, k  # tau=0.505 amplifies rounding (1.6e-13 seen)
+
+
+def test_dropin_lattice_has_the_reference_surface():
+    """Every public method of the reference's lattice class exists on lbm_b200.lattice.lattice."""
+    import inspect
+    ns = refload.load()
+    from lbm_b200.lattice import lattice as ours
+    ref_methods = [n for n, f in inspect.getmembers(ns.lattice.lattice, inspect.isfunction)
+                   if not n.startswith("_") and n != "set_default_lbm"]
+    assert len(ref_methods) >= 18
+    for n in ref_methods:
+        assert hasattr(ours, n), "missing method " + n
+        a = list(inspect.signature(getattr(ns.lattice.lattice, n)).parameters)
+        b = list(inspect.signature(getattr(ours, n)).parameters)
+        assert a == b, (n, a, b)
