@@ -126,6 +126,8 @@ class lattice:
         self._row = np.zeros(5 * self.ny + 4 * self.nx)
         self._row_dev = None            # copy of the row that is on the device
         self._cache = {}
+        self._replay = None             # per-obstacle (fx, fy) of the iteration being replayed
+        self._link_obstacles = []
         self.updates = 0                # fused updates executed
 
     def _create(self, right_wall):
@@ -393,6 +395,11 @@ class lattice:
 
     def drag_lift(self, obs, R_ref, U_ref, L_ref):
         """nb_drag_lift (lattice.py:209-214, nb.py:49-73)."""
+        if self._replay is not None:
+            # batched run (run.py): sums of this iteration were stored by the batch's updates
+            k = [i for i, o in enumerate(self._link_obstacles) if o is obs][0]
+            fx, fy = float(self._replay[k, 0]), float(self._replay[k, 1])
+            return (-2.0 * fx / (R_ref * L_ref * U_ref ** 2), -2.0 * fy / (R_ref * L_ref * U_ref ** 2))
         if self._state != "streamed":
             raise C.LbmError(-3, "drag_lift() must follow set_bc")
         if not any(o is obs for o in self._obstacles):
@@ -406,6 +413,67 @@ class lattice:
         Cx = -2.0 * fx / (R_ref * L_ref * U_ref ** 2)
         Cy = -2.0 * fy / (R_ref * L_ref * U_ref ** 2)
         return Cx, Cy
+
+    # ------------------------------------------------------------------------------------
+    # batched execution (used by lbm_b200.run.run)
+    # ------------------------------------------------------------------------------------
+    def snapshot_walls(self):
+        """The wall row the zou_he_* calls of one set_bc would record from the current arrays."""
+        row = np.empty_like(self._row)
+        nx, ny = self.nx, self.ny
+        row[0:2 * ny] = self.u_left.reshape(-1)
+        row[2 * ny:4 * ny] = self.u_right.reshape(-1)
+        row[4 * ny:4 * ny + 2 * nx] = self.u_top.reshape(-1)
+        row[4 * ny + 2 * nx:4 * ny + 4 * nx] = self.u_bot.reshape(-1)
+        row[4 * ny + 4 * nx:] = self.rho_right
+        return row
+
+    def batch_updates(self, rows):
+        """len(rows) fused updates in one library call; update k uses wall row rows[k].  Must follow a
+        completed set_bc (state 'streamed').  Leaves the lattice in the state macro() leaves it in, with
+        rho/u of the LAST update stored.  Returns the momentum-exchange sums [n, n_obs, 2] (slot k =
+        iteration preceding update k)."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "batch_updates() must follow set_bc")
+        self._need_all_bcs()
+        self._push_links()
+        h = self._handle()
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, self._row.size)
+        n = rows.shape[0]
+        C.check(self._L.lbm_set_walls(h, n, self._ptr(rows)))
+        C.check(self._L.lbm_sync(h))
+        self._row_dev = None
+        C.check(self._L.lbm_step(h, n, 0, 1, C.LBM_STEP_MACRO_LAST))
+        nobs = max(len(self._link_obstacles), 1)
+        forces = np.zeros((n, nobs, 2))
+        C.check(self._L.lbm_get_forces(h, 0, n, self._ptr(forces)))
+        self.updates += n
+        self._state = "macro_done"
+        self._cache = {}
+        return forces
+
+    def forces_now(self):
+        """[n_obs, 2] momentum-exchange sums of the current post-collision array."""
+        self._push_links()
+        out = np.zeros((max(len(self._link_obstacles), 1), 2))
+        C.check(self._L.lbm_forces_now(self._handle(), self._ptr(out)))
+        return out
+
+    def save_state(self):
+        """Device-side copy of the current post-collision populations (for exact stop-rule rollback)."""
+        cur = C.c_vp()
+        C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
+        src = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
+        if getattr(self, "_saved", None) is None:
+            self._saved = self._torch.empty_like(src)
+        self._saved.copy_(src)
+
+    def restore_state(self):
+        cur = C.c_vp()
+        C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
+        dst = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
+        dst.copy_(self._saved)
+        self._cache = {}
 
     # ------------------------------------------------------------------------------------
     # host helpers of the reference class that the apps call

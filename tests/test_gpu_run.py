@@ -1,0 +1,92 @@
+"""GPU: the batched driver (lbm_b200.run.run) reproduces the per-phase loop: same final fields,
+same per-iteration drag/lift, same stop iteration for a force-dependent stop rule."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from lbm_b200 import cases
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _turek30(cls=cases.Turek, **kw):
+    z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+    return cls(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])], **kw)
+
+
+class ObsStop(cases.Turek):
+    """Force-dependent stop rule (the reference's 'obs' mode, base_app.py:63-67): stop as soon as the
+    drag changes by less than 2e-4 between two iterations, after the ramp."""
+    stop = "obs"
+
+    def check_stop(self, it):
+        f = self.forces
+        return not (len(f) > 40 and abs(f[-1][0] - f[-2][0]) < 2.0e-4)
+
+
+@pytest.mark.parametrize("batch", [1, 7, 64])
+def test_batched_run_equals_per_phase_loop(batch):
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+    cg, co = _turek30(), _turek30()
+    cg.it_max = co.it_max = 130
+    lg = lattice(cg, make_dirs=False, arith="strict")
+    n = run(lg, cg, batch=batch, quiet=True)
+    lo = orc.OracleLattice(co)
+    n_ref = orc.run_loop(lo, co)
+    assert n == n_ref == 131
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
+    f, fo = np.array(cg.forces), np.array(co.forces)
+    assert f.shape == fo.shape == (131, 2)
+    assert np.max(np.abs(f - fo)) <= 1e-13 * np.max(np.abs(fo))
+
+
+def test_batched_run_stops_on_the_same_iteration():
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+    cg, co = _turek30(ObsStop), _turek30(ObsStop)
+    lg = lattice(cg, make_dirs=False, arith="strict")
+    n = run(lg, cg, batch=50, quiet=True)
+    lo = orc.OracleLattice(co)
+    n_ref = orc.run_loop(lo, co)
+    assert n == n_ref and 41 < n < 5000
+    assert n % 50 not in (0, 1)          # the rule fired inside a batch, so the rollback path ran
+    assert len(cg.forces) == len(co.forces) == n
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
+
+
+def test_outputs_see_the_fields_of_their_iteration():
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+
+    class Probe(cases.Cavity):
+        def outputs(self, lat, it):
+            if it % self.output_freq == 0:
+                self.seen.append((it, lat.u.copy(), lat.rho.copy()))
+    cg, co = Probe(L_lbm=32, sigma=20), Probe(L_lbm=32, sigma=20)
+    for c in (cg, co):
+        c.output_freq, c.seen, c.it_max = 25, [], 90
+    lg = lattice(cg, make_dirs=False, arith="strict")
+    run(lg, cg, batch=40, quiet=True)
+    lo = orc.OracleLattice(co)
+    co.initialize(lo)
+    for it in range(91):                    # run.py order, with outputs after macro
+        co.set_inlets(lo, it)
+        lo.macro()
+        co.outputs(lo, it)
+        lo.equilibrium(); lo.collision_stream(); co.set_bc(lo)
+    assert [s[0] for s in cg.seen] == [s[0] for s in co.seen] == [0, 25, 50, 75]
+    for a, b in zip(cg.seen, co.seen):
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    vx, uy = cg.line_fields(lg)
+    vxo, uyo = co.line_fields(lo)
+    assert np.array_equal(vx, vxo) and np.array_equal(uy, uyo)
