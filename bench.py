@@ -193,6 +193,19 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, K, W = args.nx, args.ny, args.steps, args.warmup
     s = SlabSolver(nx, ny, TAU, dist, rank, world, local, dtype=args.dtype, overlap=not args.no_overlap)
+    temporal = not args.no_temporal
+    depth = 2 if temporal else 1
+
+    def advance(first_row, n):
+        """n lattice updates; with temporal blocking consecutive updates are paired into one launch."""
+        k = 0
+        while k < n:
+            if temporal and k + 1 < n:
+                s.update2(first_row + k, first_row + k + 1, next_depth=depth)
+                k += 2
+            else:
+                s.update(first_row + k, next_depth=depth)
+                k += 1
     dev = torch.device("cuda", local)
 
     def barrier():
@@ -219,11 +232,10 @@ def gpu_arm(args):
     rows = lid_rows(s, nx, ny, list(range(n_rows)), row_len)
     s.init_equilibrium(1.0)
     s.set_walls(rows)                       # resident before the timed region
-    s.update(0)                             # iteration 0: collide-only
+    s.update(0, next_depth=depth)           # iteration 0: collide-only
     if world > 1:                           # NCCL channel set-up outside the timed region
-        s.update(0)
-    for it in range(W):
-        s.update(it)
+        s.update(0, next_depth=depth)
+    advance(0, W)
     s.finish()
     barrier()
 
@@ -237,8 +249,7 @@ def gpu_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record(s.compute)
-    for it in range(K):
-        s.update(W + it)
+    advance(W, K)
     s.finish()
     e1.record(s.compute)
     torch.cuda.synchronize(dev)
@@ -260,20 +271,27 @@ def gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for it in range(Ke):
-        s.set_walls(pinned[it:it + 1])
-        s.update(0)
+    per = 2 if temporal else 1               # updates per launch = per e2e step
+    it = 0
+    while it < Ke:
+        m = min(per, Ke - it)
+        s.set_walls(pinned[it:it + m])
+        if m == 2:
+            s.update2(0, 1, next_depth=depth)
+        else:
+            s.update(0, next_depth=depth)
         s.finish()
-        line_y = s.s.probe_line(1, ymid, 0)                 # row y = ny/2, this slab's columns
+        line_y = s.s.probe_line(1, ymid, m - 1)             # row y = ny/2, this slab's columns
         d2h = line_y.nbytes
         if owns_mid:
-            line_x = s.s.probe_line(0, xmid - s.x0, 0)      # column x = nx/2
+            line_x = s.s.probe_line(0, xmid - s.x0, m - 1)  # column x = nx/2
             d2h += line_x.nbytes
+        it += m
     torch.cuda.synchronize(dev)
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = nx * ny * Ke / t_e2e / 1e6
-    h2d = int(sum_over_ranks(row_len * 8))
+    h2d = int(sum_over_ranks(row_len * 8 * per))
     d2h = int(sum_over_ranks(d2h))
 
     bpl = BYTES_PER_LUP[args.dtype]
@@ -286,14 +304,18 @@ def gpu_arm(args):
                                   % (nx, ny, args.dtype, TAU, world),
                       "parallelism": "slab%d" % world, "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed"
                                   % (2 * 9 * s.nxl * ny * (8 if args.dtype == "f64" else 4) / 1e9),
-                      "halo_overlap": bool(s.overlap)},
+                      "halo_overlap": bool(s.overlap),
+                      "temporal_blocking": "2 updates per launch (step2_kernel)" if temporal else "off"},
            "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "note": "per step: pinned-host wall profiles -> device, one update, centre-line rho/u -> host; "
-                           "populations stay resident as in the reference's in-place time stepping"},
+                   "updates_per_step": per,
+                   "note": "per launch (%d update(s)): pinned-host wall profiles -> device, the update(s), centre-line "
+                           "rho/u -> host; byte counts are per launch; populations stay resident as in the "
+                           "reference's in-place time stepping" % per},
            "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": profiled_traffic(nx, ny, args.dtype, world), "peak_source": peak_src,
-                        "bytes_per_lattice_update": bpl, "kernel": "lbm::step_kernel<%s,fused>" % args.dtype,
+                        "bytes_per_lattice_update": bpl, "kernel": ("lbm::step2_kernel<%s,fused,16,64> (two updates per launch: bytes per launch = 2 x 144 B x cells)"
+                                   if temporal else "lbm::step_kernel<%s,fused>") % args.dtype,
                         "per": "rank 0 slab, bytes per launch / (timed region / launches)"},
            "clocks": clocks}
     if rank == 0:
@@ -320,6 +342,7 @@ def main():
     ap.add_argument("--ny", type=int, default=32768)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-temporal", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -85,14 +85,15 @@ typedef struct lbm_cfg {
 } lbm_cfg;
 
 /* Memory layout of one population buffer, for callers that allocate it themselves (torch) and
- * for the slab halo exchange: element (q, x, y), x in [-1, nxl] (x = -1 and x = nxl are the halo
- * columns), lives at element offset  origin + q*plane + x*pitch + y. */
+ * for the slab halo exchange: element (q, x, y), x in [-halo, nxl+halo) (x < 0 and x >= nxl are the
+ * halo columns), lives at element offset  origin + q*plane + x*pitch + y. */
 typedef struct lbm_layout {
     int64_t elems;  /* elements in one buffer */
     int64_t origin; /* offset of (q=0, x=0, y=0) */
     int64_t plane;  /* elements between consecutive q */
     int64_t pitch;  /* elements between consecutive x */
     int64_t elem_size;
+    int64_t halo;   /* halo columns on each side (2) */
 } lbm_layout;
 
 int lbm_abi_version(void);
@@ -146,6 +147,12 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
  * flipping the buffers; lbm_flip makes the written buffer current.  slot = force slot. */
 int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot, uint32_t flags);
 int lbm_flip(lbm_t *h);
+/* Two consecutive updates (wall rows row1, row2) of local columns [xa, xb) in ONE launch
+ * (temporal blocking through shared memory), without flipping; reads columns xa-2 .. xb+1.
+ * Not available with obstacle links.  lbm_step pairs updates this way by itself unless
+ * lbm_set_temporal_blocking(h, 0) was called. */
+int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2);
+int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
 
 /* Stream + (I)BB + Zou-He of the current F with wall row `row`, no collision: materialises the
  * reference's g (nb_col_str stream part + set_bc) in the other buffer, overwrites rho,u on the

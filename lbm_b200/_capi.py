@@ -30,7 +30,7 @@ class LbmCfg(ctypes.Structure):
 
 class LbmLayout(ctypes.Structure):
     _fields_ = [("elems", c_i64), ("origin", c_i64), ("plane", c_i64), ("pitch", c_i64),
-                ("elem_size", c_i64)]
+                ("elem_size", c_i64), ("halo", c_i64)]
 
 
 class LbmError(RuntimeError):
@@ -60,6 +60,8 @@ SIGNATURES = {
     "lbm_step": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, ctypes.c_uint32]),
     "lbm_step_columns": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_uint32]),
     "lbm_flip": (ctypes.c_int, [c_vp]),
+    "lbm_step2_columns": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64]),
+    "lbm_set_temporal_blocking": (ctypes.c_int, [c_vp, c_i32]),
     "lbm_apply_bc": (ctypes.c_int, [c_vp, c_i64]),
     "lbm_get_forces": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "lbm_forces_now": (ctypes.c_int, [c_vp, c_vp]),

@@ -1,0 +1,372 @@
+// kernels.cuh -- sm_100a kernels of the D2Q9 time step.
+//
+//   step_kernel   one lattice update per launch: pull-stream from the post-collision array F,
+//                 obstacle (I)BB (link blocks), Zou-He walls/corners, macro, equilibrium, TRT, store.
+//   step2_kernel  TWO lattice updates per launch (temporal blocking): a thread block computes the
+//                 first update on its tile plus a one-cell rim into shared memory and the second
+//                 update from shared memory, so the populations cross HBM once per two updates.
+//                 Same per-cell device functions, hence bit-identical to two step_kernel launches.
+//
+// Indexing: every population plane is addressed as  base_q[idx]  with a 32-bit cell index
+// idx = x*pitch + y and per-plane base pointers that live in the kernel parameters (constant
+// bank); the pull shift -c_q is folded into the base pointer on the host.  One IMAD.WIDE per
+// access instead of 64-bit index arithmetic per population.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "d2q9.cuh"
+
+namespace lbm {
+
+enum Mode { kFused = 0, kCollideOnly = 1, kStreamOnly = 2 };
+constexpr int kBlock = 256;
+constexpr int kHalo = 2;       // halo columns on each side of a slab (2: temporal blocking)
+
+template <typename T> struct StepParams {
+    const T *pull[9];       // pull[q][x*pitch + y] == F_q(x - cx_q, y - cy_q)   (local x, may be -1 .. nxl)
+    const T *ctr[9];        // ctr[q][x*pitch + y]  == F_q(x, y)
+    T *dst[9];              // dst[q][x*pitch + y]  == F'_q(x, y)
+    int pitch;              // elements between x columns
+    int nxl, ny;            // local slab width, height
+    int xa, xb;             // local columns processed [xa, xb)
+    int x_wl, x_wr;         // local column of the global left / right wall (out of range if not in this slab)
+    int x_lo, x_hi;         // local columns that exist in the global lattice: [x_lo, x_hi) within [-2, nxl+2)
+    int gx0, gnx;           // global column of local x = 0, global width
+    Coef<T> coef;
+    const T *walls;         // wall row of this update: u_left[2][ny] u_right[2][ny] u_top[2][gnx] u_bot[2][gnx] rho_right[ny]
+    const T *walls2;        // step2_kernel: wall row of the second update
+    T *rho_out, *u_out, *uy_out;  // optional macro output (pitched [nxl][pitch]; u_out = x component, uy_out = y)
+    const unsigned char *mask;  // optional: nonzero = cell is handled by the link blocks
+    int right_pressure;
+    int write_macro;
+};
+
+struct LinkParams {
+    int n_cells;            // distinct boundary cells in this slab
+    int n_links;
+    int n_obs;
+    const int *cell_x, *cell_y, *cell_off;   // [n_cells], [n_cells], [n_cells+1]
+    const int *link_q;                       // [n_links] direction fluid -> solid
+    const int *link_kind;                    // 0 plain BB, 1 IBB p<1/2, 2 IBB p>=1/2
+    const int *link_slot;                    // position in the caller's concatenated list
+    const void *link_c;                      // [n_links][3] coefficients (T)
+    const int *obs_off;                      // [n_obs+1] ranges of the caller's list
+    double *link_f;                          // [n_links_total][2] per-link momentum exchange
+    double *forces;                          // [n_obs][2] output slot
+    unsigned int *done;                      // block completion counter
+    int n_link_blocks;
+};
+
+// ---- population sources ------------------------------------------------------------------
+// A source hands out the nine populations ARRIVING at cell (x, y): G_q = F_q((x,y) - c_q).
+// Entries with no in-domain source are garbage and are overwritten by the wall code
+// (SURVEY.md section 9.3).
+template <typename T> struct GlobalSource {
+    const StepParams<T> &p;
+    __device__ __forceinline__ void operator()(int x, int y, T (&G)[9]) const
+    {
+        const int idx = x * p.pitch + y;
+#pragma unroll
+        for (int q = 0; q < 9; q++) G[q] = __ldg(p.pull[q] + idx);
+    }
+};
+
+template <typename T, int SP, int NS> struct SharedSource {
+    const T *f;             // [9][NS], cell (xr, yr) at xr*SP + yr
+    int x0, y0;             // lattice coordinates of (xr, yr) = (0, 0)
+    __device__ __forceinline__ void operator()(int x, int y, T (&G)[9]) const
+    {
+        const int i = (x - x0) * SP + (y - y0);
+#pragma unroll
+        for (int q = 0; q < 9; q++) G[q] = f[q * NS + i - cx_of(q) * SP - cy_of(q)];
+    }
+};
+
+// Wall / corner treatment of the streamed populations of cell (x, y).  Returns true when the
+// cell is on a wall; then (r, ux, uy) are what the reference writes into rho/u there.
+// Corner cells copy rho and u from the x-neighbour on the same horizontal wall
+// (nb.py:254-257 and siblings); its Zou-He density is recomputed here from the source.
+template <typename A, typename T, typename Src>
+__device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *walls, const Src &src,
+                                            int x, int y, T (&G)[9], T &r, T &ux, T &uy)
+{
+    const bool L = x == p.x_wl, R = x == p.x_wr, B = y == 0, Tp = y == p.ny - 1;
+    if (!(L | R | B | Tp)) return false;
+    const int gx = p.gx0 + x;
+    const T *ul = walls, *ur = ul + 2 * p.ny, *ut = ur + 2 * p.ny, *ub = ut + 2 * p.gnx,
+            *rr = ub + 2 * p.gnx;
+    if ((L | R) & (B | Tp)) {
+        const int xn = L ? x + 1 : x - 1;
+        const int gxn = L ? gx + 1 : gx - 1;
+        const T *uw = B ? ub : ut;
+        ux = uw[gxn];
+        uy = uw[p.gnx + gxn];
+        T N[9];
+        src(xn, B ? 0 : p.ny - 1, N);
+        r = B ? ZouHe<A, T>::bottom_rho(N[0], N[1], N[2], N[4], N[6], N[8], uy)
+              : ZouHe<A, T>::top_rho(N[0], N[1], N[2], N[3], N[5], N[7], uy);
+        ZouHe<A, T>::corner(G, L, B, r, ux, uy);
+    } else if (B) {
+        ux = ub[gx]; uy = ub[p.gnx + gx];
+        ZouHe<A, T>::bottom(G, ux, uy, r);
+    } else if (Tp) {
+        ux = ut[gx]; uy = ut[p.gnx + gx];
+        ZouHe<A, T>::top(G, ux, uy, r);
+    } else if (L) {
+        ux = ul[y]; uy = ul[p.ny + y];
+        ZouHe<A, T>::left(G, ux, uy, r);
+    } else {
+        ux = ur[y]; uy = ur[p.ny + y];
+        r = rr[y];  // only used by the pressure variant
+        ZouHe<A, T>::right(G, ux, uy, r, p.right_pressure != 0);
+    }
+    return true;
+}
+
+// Everything after the populations of a cell are in registers: walls, macro, collision, store.
+template <typename T, bool STRICT, int MODE>
+__device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y, T (&G)[9])
+{
+    using A = Ar<T, STRICT>;
+    const int idx = x * p.pitch + y;
+    if (MODE != kCollideOnly) {
+        T r, ux, uy;
+        const bool on_wall = apply_walls<A, T>(p, p.walls, GlobalSource<T>{p}, x, y, G, r, ux, uy);
+        if (MODE == kStreamOnly) {
+            if (on_wall && p.rho_out) {
+                p.rho_out[idx] = r;
+                p.u_out[idx] = ux;
+                p.uy_out[idx] = uy;
+            }
+        }
+    }
+    if (MODE != kStreamOnly) {
+        T r, ux, uy;
+        macro<A, T>(G, r, ux, uy);
+        if (p.write_macro) {
+            p.rho_out[idx] = r;
+            p.u_out[idx] = ux;
+            p.uy_out[idx] = uy;
+        }
+        collide<A, T>(G, r, ux, uy, p.coef);
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+}
+
+// ---------------------------------------------------------------------------------------
+// Obstacle links: one thread per distinct boundary cell (the extra blocks of the step kernel)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
+__device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
+{
+    using A = Ar<T, STRICT>;
+    const int c = block * nthreads + threadIdx.x;
+    if (c < lp.n_cells) {
+        const int x = lp.cell_x[c], y = lp.cell_y[c];
+        const int idx = x * p.pitch + y;
+        T G[9];
+        if (!FORCE_ONLY) GlobalSource<T>{p}(x, y, G);
+        const T *coef = static_cast<const T *>(lp.link_c);
+        for (int l = lp.cell_off[c]; l < lp.cell_off[c + 1]; l++) {
+            const int q = lp.link_q[l], qb = opp(q), kind = lp.link_kind[l];
+            const int o1 = kCx[qb] * p.pitch + kCy[qb];            // (im, jm) = (i, j) + c_qbar
+            const T *Fq = p.ctr[q] + idx, *Fb = p.ctr[qb] + idx;
+            const T a = __ldg(Fq);
+            const T c0 = coef[3 * l], c1 = coef[3 * l + 1], c2 = coef[3 * l + 2];
+            T val;
+            if (kind == 1)        // nb.py:98-100
+                val = A::sub(A::add(A::mul(c0, a), A::mul(c1, __ldg(Fq + o1))), A::mul(c2, __ldg(Fq + 2 * o1)));
+            else if (kind == 2)   // nb.py:102-104
+                val = A::add(A::add(A::mul(c0, a), A::mul(c1, __ldg(Fb))), A::mul(c2, __ldg(Fb + o1)));
+            else                  // nb.py:117
+                val = a;
+            if (!FORCE_ONLY) {
+#pragma unroll
+                for (int k = 1; k < 9; k++)
+                    if (k == qb) G[k] = val;
+            }
+            // nb.py:64-67: (g_up_q + g_qbar) c_q
+            const T g0 = A::add(a, val);
+            const int s = lp.link_slot[l];
+            lp.link_f[2 * s] = (double)A::mul(g0, T(kCx[q]));
+            lp.link_f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
+        }
+        if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
+    }
+    // last block done: fixed-order reduction of the per-link terms, per obstacle
+    __shared__ bool last;
+    __shared__ double red[2][kBlock];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int o = 0; o < lp.n_obs; o++) {
+        double fx = 0.0, fy = 0.0;
+        for (int k = lp.obs_off[o] + threadIdx.x; k < lp.obs_off[o + 1]; k += nthreads) {
+            fx += __ldcg(lp.link_f + 2 * k);
+            fy += __ldcg(lp.link_f + 2 * k + 1);
+        }
+        red[0][threadIdx.x] = fx;
+        red[1][threadIdx.x] = fy;
+        __syncthreads();
+        for (int s = nthreads / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                red[0][threadIdx.x] += red[0][threadIdx.x + s];
+                red[1][threadIdx.x] += red[1][threadIdx.x + s];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            lp.forces[2 * o] = red[0][0];
+            lp.forces[2 * o + 1] = red[1][0];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *lp.done = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// One update per launch.  grid.x = y tiles, grid.y = local columns xa..xb-1 (+ link blocks
+// appended along grid.y when obstacles are present); one thread per cell, threadIdx.x along y
+// (the contiguous axis) so every population plane is read and written as full 128 B lines.
+// ---------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
+{
+    const int ncols = p.xb - p.xa;
+    if ((int)blockIdx.y >= ncols) {
+        if (MODE != kCollideOnly) {
+            const int b = ((int)blockIdx.y - ncols) * gridDim.x + blockIdx.x;
+            if (b < lp.n_link_blocks) link_block<T, STRICT, MODE, false>(p, lp, b, kBlock);
+        }
+        return;
+    }
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = p.xa + blockIdx.y;
+    if (y >= p.ny) return;
+    const int idx = x * p.pitch + y;
+    if (MODE != kCollideOnly && p.mask && p.mask[idx]) return;
+    T G[9];
+    if (MODE == kCollideOnly) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) G[q] = __ldg(p.ctr[q] + idx);
+    } else {
+        GlobalSource<T>{p}(x, y, G);
+    }
+    finish_cell<T, STRICT, MODE>(p, x, y, G);
+}
+
+// ---------------------------------------------------------------------------------------
+// Two updates per launch (temporal blocking).  Tile = TX columns x TY rows; phase 1 computes the
+// first update on the tile plus a one-cell rim ((TX+2) x (TY+2) cells, pulled from global memory,
+// i.e. from the tile plus a two-cell rim) into shared memory; phase 2 computes the second update
+// of the tile from shared memory and stores it.  Rim cells outside the global lattice are skipped:
+// nothing reads them that Zou-He does not overwrite.  No obstacles, no macro output on this path.
+// ---------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int TX, int TY>
+__global__ void __launch_bounds__(kBlock, 2)
+step2_kernel(const __grid_constant__ StepParams<T> p)
+{
+    using A = Ar<T, STRICT>;
+    constexpr int SX = TX + 2, SP = TY + 2, NS = SX * SP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *f = reinterpret_cast<T *>(smem_raw);
+    const int tx0 = p.xa + blockIdx.y * TX, ty0 = blockIdx.x * TY;
+    const int txe = min(tx0 + TX, p.xb);                 // tile columns [tx0, txe)
+    const GlobalSource<T> gsrc{p};
+
+    // ---- phase 1: first update on the rimmed tile -> shared memory --------------------------
+    const int r_lo = max(tx0 - 1, p.x_lo), r_hi = min(txe + 1, p.x_hi);
+    for (int c = threadIdx.x; c < NS; c += kBlock) {
+        const int xr = c / SP, yr = c - xr * SP;
+        const int x = tx0 - 1 + xr, y = ty0 - 1 + yr;
+        if (x < r_lo || x >= r_hi || y < 0 || y >= p.ny) continue;
+        T G[9], r, ux, uy;
+        gsrc(x, y, G);
+        apply_walls<A, T>(p, p.walls, gsrc, x, y, G, r, ux, uy);
+        macro<A, T>(G, r, ux, uy);
+        collide<A, T>(G, r, ux, uy, p.coef);
+#pragma unroll
+        for (int q = 0; q < 9; q++) f[q * NS + c] = G[q];
+    }
+    __syncthreads();
+
+    // ---- phase 2: second update of the tile from shared memory -> global ----------------------
+    const SharedSource<T, SP, NS> ssrc{f, tx0 - 1, ty0 - 1};
+    for (int c = threadIdx.x; c < TX * TY; c += kBlock) {
+        const int xt = c / TY, yt = c - xt * TY;
+        const int x = tx0 + xt, y = ty0 + yt;
+        if (x >= txe || y >= p.ny) continue;
+        T G[9], r, ux, uy;
+        ssrc(x, y, G);
+        apply_walls<A, T>(p, p.walls2, ssrc, x, y, G, r, ux, uy);
+        macro<A, T>(G, r, ux, uy);
+        collide<A, T>(G, r, ux, uy, p.coef);
+        const int idx = x * p.pitch + y;
+#pragma unroll
+        for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+    }
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+force_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
+{
+    link_block<T, STRICT, kFused, true>(p, lp, blockIdx.x, kBlock);
+}
+
+// Macroscopic fields of the streamed + boundary-treated populations along one lattice line
+// (what lattice.macro() of the next iteration computes there): axis 0 -> column x = index
+// (ny cells), axis 1 -> row y = index (nxl cells).  out = [rho | ux | uy], each n long.
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n, T *out)
+{
+    using A = Ar<T, STRICT>;
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n) return;
+    const int x = axis == 0 ? index : k, y = axis == 0 ? k : index;
+    T G[9], r, ux, uy;
+    const GlobalSource<T> gsrc{p};
+    gsrc(x, y, G);
+    apply_walls<A, T>(p, p.walls, gsrc, x, y, G, r, ux, uy);
+    macro<A, T>(G, r, ux, uy);
+    out[k] = r;
+    out[n + k] = ux;
+    out[2 * n + k] = uy;
+}
+
+// uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+init_kernel(T *dst, long long plane, int pitch, int nxl, int ny, T r, T ux, T uy)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = blockIdx.y;
+    if (y >= ny) return;
+    T E[9];
+    equilibrium<Ar<T, STRICT>, T>(E, r, ux, uy);
+#pragma unroll
+    for (int q = 0; q < 9; q++) dst[q * plane + (long long)x * pitch + y] = E[q];
+}
+
+// nb_equilibrium on pitched device fields
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(kBlock)
+equilibrium_kernel(T *dst, long long plane, int pitch, int nxl, int ny, const T *rho, const T *u)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    const int x = blockIdx.y;
+    if (y >= ny) return;
+    const long long cell = (long long)x * pitch + y;
+    T E[9];
+    equilibrium<Ar<T, STRICT>, T>(E, rho[cell], u[cell], u[(long long)nxl * pitch + cell]);
+#pragma unroll
+    for (int q = 0; q < 9; q++) dst[q * plane + cell] = E[q];
+}
+
+}  // namespace lbm

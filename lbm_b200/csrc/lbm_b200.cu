@@ -14,309 +14,8 @@
 #include <vector>
 
 #include "../../include/lbm_b200.h"
-#include "d2q9.cuh"
 
-namespace lbm {
-
-enum Mode { kFused = 0, kCollideOnly = 1, kStreamOnly = 2 };
-
-// ---------------------------------------------------------------------------------------
-// Kernel parameters
-// ---------------------------------------------------------------------------------------
-template <typename T> struct StepParams {
-    const T *src;           // element (q=0, x=0, y=0) of the array read
-    T *dst;                 // same element of the array written
-    long long plane;        // elements between q planes
-    int pitch;              // elements between x columns
-    int nxl, ny;            // local slab width, height
-    int xa, xb;             // local columns processed [xa, xb)
-    long long gx0, gnx;     // global column of local x = 0, global width
-    Coef<T> coef;
-    const T *walls;         // wall row of this update: u_left[2][ny] u_right[2][ny] u_top[2][gnx] u_bot[2][gnx] rho_right[ny]
-    T *rho_out, *u_out;     // optional macro output (pitched [nxl][pitch], [2][nxl][pitch])
-    const unsigned char *mask;  // optional: nonzero = cell is handled by the link blocks
-    int right_pressure;
-    int write_macro;
-};
-
-struct LinkParams {
-    int n_cells;            // distinct boundary cells in this slab
-    int n_links;
-    int n_obs;
-    const int *cell_x, *cell_y, *cell_off;   // [n_cells], [n_cells], [n_cells+1]
-    const int *link_q;                       // [n_links] direction fluid -> solid
-    const int *link_kind;                    // 0 plain BB, 1 IBB p<1/2, 2 IBB p>=1/2
-    const int *link_slot;                    // position in the caller's concatenated list
-    const void *link_c;                      // [n_links][3] coefficients (T)
-    const int *obs_off;                      // [n_obs+1] ranges of the caller's list
-    double *link_f;                          // [n_links_total][2] per-link momentum exchange
-    double *forces;                          // [n_obs][2] output slot
-    unsigned int *done;                      // block completion counter
-    int n_link_blocks;
-};
-
-template <typename T> __device__ __forceinline__ T ldg(const T *p) { return __ldg(p); }
-
-// Pull the nine populations arriving at local cell (x, y).  Entries with no in-domain source
-// are garbage here and are overwritten by the wall code.
-template <typename T>
-__device__ __forceinline__ void pull(const StepParams<T> &p, int x, int y, T (&G)[9])
-{
-    const T *c = p.src + (long long)x * p.pitch + y;
-#pragma unroll
-    for (int q = 0; q < 9; q++)
-        G[q] = ldg(c + q * p.plane - cx_of(q) * p.pitch - cy_of(q));
-}
-
-template <typename T>
-__device__ __forceinline__ void load_local(const StepParams<T> &p, int x, int y, T (&G)[9])
-{
-    const T *c = p.src + (long long)x * p.pitch + y;
-#pragma unroll
-    for (int q = 0; q < 9; q++) G[q] = ldg(c + q * p.plane);
-}
-
-// Zou-He density of the off-corner cell (xn, 0) / (xn, ny-1) computed straight from F; used by
-// the corner cells, which copy rho and u from that neighbour (nb.py:254-257 and siblings).
-template <typename A, typename T>
-__device__ __forceinline__ T neighbour_wall_rho(const StepParams<T> &p, int xn, bool bottom, T uy)
-{
-    T G[9];
-    pull(p, xn, bottom ? 0 : p.ny - 1, G);
-    return bottom ? ZouHe<A, T>::bottom_rho(G[0], G[1], G[2], G[4], G[6], G[8], uy)
-                  : ZouHe<A, T>::top_rho(G[0], G[1], G[2], G[3], G[5], G[7], uy);
-}
-
-// Wall / corner treatment of the streamed populations of cell (x, y).  Returns true when the
-// cell is on a wall; then (r, ux, uy) are what the reference writes into rho/u there.
-template <typename A, typename T>
-__device__ __forceinline__ bool apply_walls(const StepParams<T> &p, int x, int y, T (&G)[9], T &r,
-                                            T &ux, T &uy)
-{
-    const long long gx = p.gx0 + x;
-    const bool L = gx == 0, R = gx == p.gnx - 1, B = y == 0, Tp = y == p.ny - 1;
-    if (!(L | R | B | Tp)) return false;
-    const T *ul = p.walls, *ur = ul + 2 * p.ny, *ut = ur + 2 * p.ny, *ub = ut + 2 * p.gnx,
-            *rr = ub + 2 * p.gnx;
-    if ((L | R) & (B | Tp)) {
-        // corner: neighbour on the same horizontal wall
-        const int xn = L ? x + 1 : x - 1;
-        const long long gxn = L ? gx + 1 : gx - 1;
-        const T *uw = B ? ub : ut;
-        ux = uw[gxn];
-        uy = uw[p.gnx + gxn];
-        r = neighbour_wall_rho<A, T>(p, xn, B, uy);
-        ZouHe<A, T>::corner(G, L, B, r, ux, uy);
-    } else if (B) {
-        ux = ub[gx]; uy = ub[p.gnx + gx];
-        ZouHe<A, T>::bottom(G, ux, uy, r);
-    } else if (Tp) {
-        ux = ut[gx]; uy = ut[p.gnx + gx];
-        ZouHe<A, T>::top(G, ux, uy, r);
-    } else if (L) {
-        ux = ul[y]; uy = ul[p.ny + y];
-        ZouHe<A, T>::left(G, ux, uy, r);
-    } else {
-        ux = ur[y]; uy = ur[p.ny + y];
-        r = rr[y];  // only used by the pressure variant
-        ZouHe<A, T>::right(G, ux, uy, r, p.right_pressure != 0);
-    }
-    return true;
-}
-
-// Everything after the populations of a cell are in registers: walls, macro, collision, store.
-template <typename T, bool STRICT, int MODE>
-__device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y, T (&G)[9])
-{
-    using A = Ar<T, STRICT>;
-    const long long cell = (long long)x * p.pitch + y;
-    if (MODE != kCollideOnly) {
-        T r, ux, uy;
-        const bool on_wall = apply_walls<A, T>(p, x, y, G, r, ux, uy);
-        if (MODE == kStreamOnly) {
-            if (on_wall && p.rho_out) {
-                p.rho_out[cell] = r;
-                p.u_out[cell] = ux;
-                p.u_out[(long long)p.nxl * p.pitch + cell] = uy;
-            }
-        }
-    }
-    if (MODE != kStreamOnly) {
-        T r, ux, uy;
-        macro<A, T>(G, r, ux, uy);
-        if (p.write_macro) {
-            p.rho_out[cell] = r;
-            p.u_out[cell] = ux;
-            p.u_out[(long long)p.nxl * p.pitch + cell] = uy;
-        }
-        collide<A, T>(G, r, ux, uy, p.coef);
-    }
-    T *d = p.dst + cell;
-#pragma unroll
-    for (int q = 0; q < 9; q++) d[q * p.plane] = G[q];
-}
-
-// ---------------------------------------------------------------------------------------
-// Obstacle links: one thread per distinct boundary cell (the extra blocks of the step kernel)
-// ---------------------------------------------------------------------------------------
-template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
-__device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
-{
-    using A = Ar<T, STRICT>;
-    const int c = block * nthreads + threadIdx.x;
-    if (c < lp.n_cells) {
-        const int x = lp.cell_x[c], y = lp.cell_y[c];
-        T G[9];
-        if (!FORCE_ONLY) pull(p, x, y, G);
-        const T *ctr = p.src + (long long)x * p.pitch + y;
-        const T *coef = static_cast<const T *>(lp.link_c);
-        for (int l = lp.cell_off[c]; l < lp.cell_off[c + 1]; l++) {
-            const int q = lp.link_q[l], qb = opp(q), kind = lp.link_kind[l];
-            const int cbx = kCx[qb], cby = kCy[qb];
-            const long long o1 = (long long)cbx * p.pitch + cby;   // (im, jm) = (i, j) + c_qbar
-            const T *Fq = ctr + q * p.plane, *Fb = ctr + qb * p.plane;
-            const T a = ldg(Fq);
-            const T c0 = coef[3 * l], c1 = coef[3 * l + 1], c2 = coef[3 * l + 2];
-            T val;
-            if (kind == 1)        // nb.py:98-100
-                val = A::sub(A::add(A::mul(c0, a), A::mul(c1, ldg(Fq + o1))), A::mul(c2, ldg(Fq + 2 * o1)));
-            else if (kind == 2)   // nb.py:102-104
-                val = A::add(A::add(A::mul(c0, a), A::mul(c1, ldg(Fb))), A::mul(c2, ldg(Fb + o1)));
-            else                  // nb.py:117
-                val = a;
-            if (!FORCE_ONLY) {
-#pragma unroll
-                for (int k = 1; k < 9; k++)
-                    if (k == qb) G[k] = val;
-            }
-            // nb.py:64-67: (g_up_q + g_qbar) c_q
-            const T g0 = A::add(a, val);
-            const int s = lp.link_slot[l];
-            lp.link_f[2 * s] = (double)A::mul(g0, T(kCx[q]));
-            lp.link_f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
-        }
-        if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
-    }
-    // last block done: fixed-order reduction of the per-link terms, per obstacle
-    __shared__ bool last;
-    __shared__ double red[2][256];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int o = 0; o < lp.n_obs; o++) {
-        double fx = 0.0, fy = 0.0;
-        for (int k = lp.obs_off[o] + threadIdx.x; k < lp.obs_off[o + 1]; k += nthreads) {
-            fx += __ldcg(lp.link_f + 2 * k);
-            fy += __ldcg(lp.link_f + 2 * k + 1);
-        }
-        red[0][threadIdx.x] = fx;
-        red[1][threadIdx.x] = fy;
-        __syncthreads();
-        for (int s = nthreads / 2; s > 0; s >>= 1) {
-            if (threadIdx.x < s) {
-                red[0][threadIdx.x] += red[0][threadIdx.x + s];
-                red[1][threadIdx.x] += red[1][threadIdx.x + s];
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            lp.forces[2 * o] = red[0][0];
-            lp.forces[2 * o + 1] = red[1][0];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *lp.done = 0;
-}
-
-// ---------------------------------------------------------------------------------------
-// The step kernel.  grid.x = y tiles, grid.y = local columns xa..xb-1 (+ link blocks appended
-// along grid.y when obstacles are present); one thread per cell, threadIdx.x along y (the
-// contiguous axis) so every population plane is read and written as full 128 B lines.
-// ---------------------------------------------------------------------------------------
-constexpr int kBlock = 256;
-
-template <typename T, bool STRICT, int MODE>
-__global__ void __launch_bounds__(kBlock)
-step_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
-{
-    const int ncols = p.xb - p.xa;
-    if ((int)blockIdx.y >= ncols) {
-        if (MODE != kCollideOnly) {
-            const int b = ((int)blockIdx.y - ncols) * gridDim.x + blockIdx.x;
-            if (b < lp.n_link_blocks) link_block<T, STRICT, MODE, false>(p, lp, b, kBlock);
-        }
-        return;
-    }
-    const int y = blockIdx.x * kBlock + threadIdx.x;
-    const int x = p.xa + blockIdx.y;
-    if (y >= p.ny) return;
-    if (MODE != kCollideOnly && p.mask && p.mask[(long long)x * p.pitch + y]) return;
-    T G[9];
-    if (MODE == kCollideOnly) load_local(p, x, y, G);
-    else pull(p, x, y, G);
-    finish_cell<T, STRICT, MODE>(p, x, y, G);
-}
-
-template <typename T, bool STRICT>
-__global__ void __launch_bounds__(kBlock)
-force_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
-{
-    link_block<T, STRICT, kFused, true>(p, lp, blockIdx.x, kBlock);
-}
-
-// Macroscopic fields of the streamed + boundary-treated populations along one lattice line
-// (what lattice.macro() of the next iteration computes there): axis 0 -> column x = index
-// (ny cells), axis 1 -> row y = index (nxl cells).  out = [rho | ux | uy], each n long.
-template <typename T, bool STRICT>
-__global__ void __launch_bounds__(kBlock)
-probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n, T *out)
-{
-    using A = Ar<T, STRICT>;
-    const int k = blockIdx.x * kBlock + threadIdx.x;
-    if (k >= n) return;
-    const int x = axis == 0 ? index : k, y = axis == 0 ? k : index;
-    T G[9], r, ux, uy;
-    pull(p, x, y, G);
-    apply_walls<A, T>(p, x, y, G, r, ux, uy);
-    macro<A, T>(G, r, ux, uy);
-    out[k] = r;
-    out[n + k] = ux;
-    out[2 * n + k] = uy;
-}
-
-// uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
-template <typename T, bool STRICT>
-__global__ void __launch_bounds__(kBlock)
-init_kernel(T *dst, long long plane, int pitch, int nxl, int ny, T r, T ux, T uy)
-{
-    const int y = blockIdx.x * kBlock + threadIdx.x;
-    const int x = blockIdx.y;
-    if (y >= ny) return;
-    T E[9];
-    equilibrium<Ar<T, STRICT>, T>(E, r, ux, uy);
-#pragma unroll
-    for (int q = 0; q < 9; q++) dst[q * plane + (long long)x * pitch + y] = E[q];
-}
-
-// nb_equilibrium on pitched device fields
-template <typename T, bool STRICT>
-__global__ void __launch_bounds__(kBlock)
-equilibrium_kernel(T *dst, long long plane, int pitch, int nxl, int ny, const T *rho, const T *u)
-{
-    const int y = blockIdx.x * kBlock + threadIdx.x;
-    const int x = blockIdx.y;
-    if (y >= ny) return;
-    const long long cell = (long long)x * pitch + y;
-    T E[9];
-    equilibrium<Ar<T, STRICT>, T>(E, rho[cell], u[cell], u[(long long)nxl * pitch + cell]);
-#pragma unroll
-    for (int q = 0; q < 9; q++) dst[q * plane + cell] = E[q];
-}
-
-}  // namespace lbm
+#include "kernels.cuh"
 
 // =========================================================================================
 // Host side: handle + C ABI
@@ -354,7 +53,8 @@ struct lbm_handle {
     bool own_buf = false;
     int cur = 0;
     StateKind kind = kNone;
-    bool other_has_g = false;     // other buffer holds stream+BC of current F (lbm_apply_bc)
+    bool other_has_g = false;
+    bool temporal = true;         // pair updates into step2_kernel launches where possible     // other buffer holds stream+BC of current F (lbm_apply_bc)
     cudaStream_t stream = nullptr;
     // walls
     void *walls = nullptr;        // device table, element type T
@@ -387,10 +87,11 @@ static void compute_layout(const lbm_cfg &c, lbm_layout &l)
 {
     l.elem_size = c.dtype == LBM_F64 ? 8 : 4;
     l.pitch = round_up(c.ny, 128 / l.elem_size);
-    l.plane = (c.nxl + 2) * l.pitch;
+    l.halo = kHalo;
+    l.plane = (c.nxl + 2 * kHalo) * l.pitch;
     // one guard column before and after everything so that y-1 / y+1 pulls at the first and
     // last halo column stay inside the allocation
-    l.origin = l.pitch /*guard*/ + l.pitch /*halo column x = -1*/;
+    l.origin = l.pitch /*guard*/ + kHalo * l.pitch /*halo columns x = -2, -1*/;
     l.elems = 9 * l.plane + 2 * l.pitch;
 }
 
@@ -399,6 +100,8 @@ static int check_cfg(const lbm_cfg *c)
     if (!c) return fail(LBM_E_INVALID, "cfg is NULL");
     if (c->nx < 3 || c->ny < 3) return fail(LBM_E_INVALID, "lattice must be at least 3x3 (got %lld x %lld)", (long long)c->nx, (long long)c->ny);
     if (c->ny > (1 << 30) || c->nx > (1LL << 31) - 2) return fail(LBM_E_INVALID, "lattice too large");
+    if ((c->nxl + 2 * kHalo + 2) * round_up(c->ny, 32) >= (1LL << 31))
+        return fail(LBM_E_UNSUPPORTED, "slab of %lld x %lld cells exceeds the 32-bit cell index of one population plane; use more slabs", (long long)c->nxl, (long long)c->ny);
     if (c->x0 < 0 || c->nxl < 1 || c->x0 + c->nxl > c->nx) return fail(LBM_E_INVALID, "slab [%lld, %lld) outside [0, %lld)", (long long)c->x0, (long long)(c->x0 + c->nxl), (long long)c->nx);
     if (c->nxl < 2 && c->nxl != c->nx) return fail(LBM_E_INVALID, "slab must be at least 2 columns wide");
     if (c->dtype != LBM_F64 && c->dtype != LBM_F32) return fail(LBM_E_INVALID, "dtype must be LBM_F64 or LBM_F32");
@@ -453,16 +156,25 @@ static int ensure_forces(lbm_handle *h, int64_t n)
 template <typename T> static void fill_params(const lbm_handle *h, StepParams<T> &p, LinkParams &lp,
                                                int src, int dst, int xa, int xb, int64_t row, int64_t slot)
 {
-    p.src = static_cast<const T *>(elem_ptr(h, src, 0));
-    p.dst = static_cast<T *>(elem_ptr(h, dst, 0));
-    p.plane = h->lay.plane;
+    const T *s0 = static_cast<const T *>(elem_ptr(h, src, 0));
+    T *d0 = static_cast<T *>(elem_ptr(h, dst, 0));
+    for (int q = 0; q < 9; q++) {
+        p.ctr[q] = s0 + q * h->lay.plane;
+        p.pull[q] = p.ctr[q] - cx_of(q) * h->lay.pitch - cy_of(q);
+        p.dst[q] = d0 + q * h->lay.plane;
+    }
     p.pitch = (int)h->lay.pitch;
     p.nxl = (int)h->cfg.nxl;
     p.ny = (int)h->cfg.ny;
     p.xa = xa;
     p.xb = xb;
-    p.gx0 = h->cfg.x0;
-    p.gnx = h->cfg.nx;
+    const bool has_l = h->cfg.x0 == 0, has_r = h->cfg.x0 + h->cfg.nxl == h->cfg.nx;
+    p.x_wl = has_l ? 0 : -(1 << 30);
+    p.x_wr = has_r ? (int)h->cfg.nxl - 1 : -(1 << 30);
+    p.x_lo = has_l ? 0 : -1;
+    p.x_hi = has_r ? (int)h->cfg.nxl : (int)h->cfg.nxl + 1;
+    p.gx0 = (int)h->cfg.x0;
+    p.gnx = (int)h->cfg.nx;
     const double op = h->cfg.om_p, om = h->cfg.om_m;
     p.coef.one_m_omp = T(1.0 - op);
     p.coef.om_p = T(op);
@@ -470,8 +182,10 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.coef.a_opp = T(0.5 * (op - om));
     p.coef.a_eq = T(0.5 * (op + om));
     p.walls = h->walls ? static_cast<const T *>(h->walls) + row * h->row_len : nullptr;
+    p.walls2 = nullptr;
     p.rho_out = static_cast<T *>(h->rho);
     p.u_out = static_cast<T *>(h->u);
+    p.uy_out = h->u ? static_cast<T *>(h->u) + (size_t)h->cfg.nxl * h->lay.pitch : nullptr;
     p.mask = h->d_mask;
     p.right_pressure = h->cfg.right_wall == LBM_RIGHT_PRESSURE;
     p.write_macro = 0;
@@ -486,6 +200,47 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     lp.forces = h->d_forces ? h->d_forces + slot * std::max(h->n_obs, 1) * 2 : nullptr;
     lp.done = h->d_done;
     lp.n_link_blocks = h->n_link_blocks;
+}
+
+// ---- temporal blocking: two updates per launch ------------------------------------------
+constexpr int kTX = 16, kTY = 64;
+
+template <typename T, bool STRICT>
+static int launch_step2_t(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
+{
+    StepParams<T> p;
+    LinkParams lp;
+    fill_params<T>(h, p, lp, src, dst, xa, xb, row1, 0);
+    p.walls2 = static_cast<const T *>(h->walls) + row2 * h->row_len;
+    // a corner cell reads its x-neighbour's pulled populations from shared memory: the right wall
+    // column must not be the first column of its tile -> give the last two columns their own launch
+    if (p.x_wr >= xa + 1 && p.x_wr < xb && (p.x_wr - xa) % kTX == 0) {
+        int rc = launch_step2_t<T, STRICT>(h, src, dst, xa, p.x_wr - 1, row1, row2);
+        if (rc) return rc;
+        return launch_step2_t<T, STRICT>(h, src, dst, p.x_wr - 1, xb, row1, row2);
+    }
+    constexpr size_t smem = 9 * (size_t)(kTX + 2) * (kTY + 2) * sizeof(T);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(step2_kernel<T, STRICT, kTX, kTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((h->cfg.ny + kTY - 1) / kTY), (unsigned)((xb - xa + kTX - 1) / kTX)), block(kBlock);
+    if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one temporal-blocking launch");
+    step2_kernel<T, STRICT, kTX, kTY><<<grid, block, smem, h->stream>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+static int launch_step2(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
+{
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    if (h->cfg.dtype == LBM_F64)
+        return strict ? launch_step2_t<double, true>(h, src, dst, xa, xb, row1, row2)
+                      : launch_step2_t<double, false>(h, src, dst, xa, xb, row1, row2);
+    return strict ? launch_step2_t<float, true>(h, src, dst, xa, xb, row1, row2)
+                  : launch_step2_t<float, false>(h, src, dst, xa, xb, row1, row2);
 }
 
 template <typename T, bool STRICT>
@@ -907,6 +662,16 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         const bool last = s == n_updates - 1;
         const bool wm = last && (flags & LBM_STEP_MACRO_LAST);
         const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
+        // two updates in one launch when neither needs obstacle links or macro output
+        const bool wm_next = (s + 1 == n_updates - 1) && (flags & LBM_STEP_MACRO_LAST);
+        if (h->temporal && mode == kFused && h->n_obs == 0 && s + 1 < n_updates && !wm_next && h->cfg.nxl >= 4) {
+            rc = launch_step2(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride,
+                              first_row + (s + 1) * row_stride);
+            if (rc) return rc;
+            h->cur ^= 1;
+            s++;
+            continue;
+        }
         rc = launch_step(h, mode, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride, s, wm);
         if (rc) return rc;
         h->cur ^= 1;
@@ -931,6 +696,25 @@ int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot
     const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
     if (mode == kFused) { rc = check_row(h, row); if (rc) return rc; }
     return launch_step(h, mode, h->cur, h->cur ^ 1, (int)xa, (int)xb, row, slot, (flags & LBM_STEP_MACRO_LAST) != 0);
+}
+
+int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2)
+{
+    CHECK_H(h);
+    if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_step2_columns needs post-collision populations");
+    if (h->n_obs > 0) return fail(LBM_E_UNSUPPORTED, "two-update launches do not handle obstacle links");
+    if (xa < 0 || xb > h->cfg.nxl || xb - xa < 2) return fail(LBM_E_INVALID, "bad column range (need at least 2 columns)");
+    int rc = check_row(h, row1);
+    if (!rc) rc = check_row(h, row2);
+    if (rc) return rc;
+    return launch_step2(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, row1, row2);
+}
+
+int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)
+{
+    if (!h) return fail(LBM_E_INVALID, "handle is NULL");
+    h->temporal = enable != 0;
+    return LBM_OK;
 }
 
 int lbm_flip(lbm_t *h)

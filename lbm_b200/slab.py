@@ -29,24 +29,37 @@ def slab_bounds(nx, world, rank):
     return x0, base + (1 if rank < rem else 0)
 
 
-def exchange_ops(view, nxl, rank, world, dist):
-    """P2P ops that fill the halo columns of `view` ([9, nxl+2, pitch], column index = x + 1)."""
+# what the neighbour needs after ONE update (its edge cells pull across the interface) and after a
+# TWO-update launch (it recomputes the first update on my edge column, section "temporal blocking"
+# of DESIGN.md).  Entries: (my column counted from the interface, populations, its halo depth).
+_PLAN1 = {"right": [(0, Q_RIGHT)], "left": [(0, Q_LEFT)]}
+_PLAN2 = {"right": [(0, (0, 3, 4) + Q_RIGHT), (1, Q_RIGHT)], "left": [(0, (0, 3, 4) + Q_LEFT), (1, Q_LEFT)]}
+
+
+def exchange_ops(view, nxl, rank, world, dist, halo=1, depth=1):
+    """P2P ops that fill the halo columns of `view` ([9, nxl+2*halo, pitch], column index = x + halo)
+    for the next launch: depth 1 = single update, depth 2 = two-update launch."""
+    plan = _PLAN1 if depth == 1 else _PLAN2
     ops = []
     if rank + 1 < world:
-        for q in Q_RIGHT:
-            ops.append(dist.P2POp(dist.isend, view[q, nxl], rank + 1))
-        for q in Q_LEFT:
-            ops.append(dist.P2POp(dist.irecv, view[q, nxl + 1], rank + 1))
+        for d, qs in plan["right"]:
+            for q in qs:
+                ops.append(dist.P2POp(dist.isend, view[q, halo + nxl - 1 - d], rank + 1))
+        for d, qs in plan["left"]:
+            for q in qs:
+                ops.append(dist.P2POp(dist.irecv, view[q, halo + nxl + d], rank + 1))
     if rank > 0:
-        for q in Q_LEFT:
-            ops.append(dist.P2POp(dist.isend, view[q, 1], rank - 1))
-        for q in Q_RIGHT:
-            ops.append(dist.P2POp(dist.irecv, view[q, 0], rank - 1))
+        for d, qs in plan["left"]:
+            for q in qs:
+                ops.append(dist.P2POp(dist.isend, view[q, halo + d], rank - 1))
+        for d, qs in plan["right"]:
+            for q in qs:
+                ops.append(dist.P2POp(dist.irecv, view[q, halo - 1 - d], rank - 1))
     return ops
 
 
-def exchange_halos(view, nxl, rank, world, dist):
-    ops = exchange_ops(view, nxl, rank, world, dist)
+def exchange_halos(view, nxl, rank, world, dist, halo=1, depth=1):
+    ops = exchange_ops(view, nxl, rank, world, dist, halo, depth)
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -69,6 +82,7 @@ class SlabSolver:
                         device=device, x0=self.x0, nxl=self.nxl, stream=self.compute)
         self.overlap = overlap and world > 1 and self.nxl >= 4
         self._halo_ready = None
+        self.edge = 16                   # columns of the edge launches of update2 (one tile)
         self.updates = 0
 
     def init_equilibrium(self, rho=1.0):
@@ -77,35 +91,65 @@ class SlabSolver:
     def set_walls(self, rows):
         self.s.set_walls(rows)
 
-    def update(self, row=0):
-        """One lattice update of the whole (distributed) domain."""
+    def _exchange(self, oth, after, depth):
+        torch = self.torch
+        self.comm.wait_event(after)
+        with torch.cuda.stream(self.comm):
+            exchange_halos(oth, self.nxl, self.rank, self.world, self.dist, self.s.layout.halo, depth)
+            self._halo_ready = torch.cuda.Event()
+            self._halo_ready.record(self.comm)
+
+    def update(self, row=0, next_depth=1):
+        """One lattice update of the whole (distributed) domain; next_depth = 2 if the next launch is a
+        two-update one (it needs a deeper halo)."""
         torch = self.torch
         s, nxl = self.s, self.nxl
         if self.world == 1:
-            s.step(1, row, 0)
+            s.step_columns(0, nxl, row)
+            s.flip()
             self.updates += 1
             return
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)       # halos of the current array have landed
-        _, oth = self.s.views()
+        _, oth = s.views()
+        ev = torch.cuda.Event()
         if self.overlap:
-            s.step_columns(0, 1, row)
-            s.step_columns(nxl - 1, nxl, row)
-            edges_done = torch.cuda.Event()
-            edges_done.record(self.compute)
-            s.step_columns(1, nxl - 1, row)
-            self.comm.wait_event(edges_done)
+            s.step_columns(0, 2, row)
+            s.step_columns(nxl - 2, nxl, row)
+            ev.record(self.compute)
+            s.step_columns(2, nxl - 2, row)
         else:
             s.step_columns(0, nxl, row)
-            done = torch.cuda.Event()
-            done.record(self.compute)
-            self.comm.wait_event(done)
-        with torch.cuda.stream(self.comm):
-            exchange_halos(oth, nxl, self.rank, self.world, self.dist)
-            self._halo_ready = torch.cuda.Event()
-            self._halo_ready.record(self.comm)
+            ev.record(self.compute)
+        self._exchange(oth, ev, next_depth)
         s.flip()
         self.updates += 1
+
+    def update2(self, row1=0, row2=0, next_depth=2):
+        """Two lattice updates in one launch per column range (temporal blocking)."""
+        torch = self.torch
+        s, nxl = self.s, self.nxl
+        if self.world == 1:
+            s.step2_columns(0, nxl, row1, row2)
+            s.flip()
+            self.updates += 2
+            return
+        if self._halo_ready is not None:
+            self.compute.wait_event(self._halo_ready)
+        _, oth = s.views()
+        ev = torch.cuda.Event()
+        w = self.edge
+        if self.overlap and nxl >= 4 * w:
+            s.step2_columns(0, w, row1, row2)
+            s.step2_columns(nxl - w, nxl, row1, row2)
+            ev.record(self.compute)
+            s.step2_columns(w, nxl - w, row1, row2)
+        else:
+            s.step2_columns(0, nxl, row1, row2)
+            ev.record(self.compute)
+        self._exchange(oth, ev, next_depth)
+        s.flip()
+        self.updates += 2
 
     def finish(self):
         if self._halo_ready is not None:

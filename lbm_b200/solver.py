@@ -112,6 +112,12 @@ class Solver:
     def step_columns(self, xa, xb, row=0, slot=0):
         C.check(self._L.lbm_step_columns(self._h, xa, xb, row, slot, 0))
 
+    def step2_columns(self, xa, xb, row1=0, row2=0):
+        C.check(self._L.lbm_step2_columns(self._h, xa, xb, row1, row2))
+
+    def set_temporal_blocking(self, enable):
+        C.check(self._L.lbm_set_temporal_blocking(self._h, 1 if enable else 0))
+
     def flip(self):
         C.check(self._L.lbm_flip(self._h))
 
@@ -163,14 +169,14 @@ class Solver:
         return out
 
     def views(self):
-        """Torch views [9, nxl+2, pitch] of (current, other) population buffers; column index = x + 1
-        (index 0 and nxl+1 are the halo columns)."""
+        """Torch views [9, nxl+2*halo, pitch] of (current, other) population buffers; column index =
+        x + halo (the first and last `halo` columns are the halo)."""
         cur, oth = C.c_vp(), C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._h, ctypes.byref(cur), ctypes.byref(oth)))
         i = 0 if cur.value == self.buffers[0].data_ptr() else 1
         lay = self.layout
-        start = lay.origin - lay.pitch
+        start = lay.origin - lay.halo * lay.pitch
 
         def v(buf):
-            return buf[start:start + 9 * lay.plane].view(9, self.nxl + 2, lay.pitch)
+            return buf[start:start + 9 * lay.plane].view(9, self.nxl + 2 * lay.halo, lay.pitch)
         return v(self.buffers[i]), v(self.buffers[i ^ 1])

@@ -15,15 +15,15 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("overlap", [1, 0])
-def test_slab_equals_single_gpu(overlap):
+@pytest.mark.parametrize("overlap,temporal", [(1, 0), (0, 0), (1, 1), (0, 1)])
+def test_slab_equals_single_gpu(overlap, temporal):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs 2 GPUs")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29611 + overlap),
-           os.path.join(ROOT, "tests", "slab_worker.py"), "515", "300", "40", str(overlap)]
+           "--master-addr", "127.0.0.1", "--master-port", str(29611 + overlap + 2 * temporal),
+           os.path.join(ROOT, "tests", "slab_worker.py"), "515", "300", "41", str(overlap), str(temporal)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]

@@ -1,0 +1,86 @@
+"""GPU: the two-updates-per-launch kernel (temporal blocking) is bit-identical to two single
+updates, for every wall variant, odd sizes (tiles clipped, right wall first in its tile) and with
+time-dependent wall rows; strict arithmetic additionally equals the oracle bit for bit."""
+import numpy as np
+import pytest
+
+from lbm_b200 import cases
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows(nx, ny, n, seed, pressure):
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, 5 * ny + 4 * nx))
+    yy = np.linspace(0, 1, ny)
+    for k in range(n):
+        a = 1.0 - np.exp(-(k + 1) ** 2 / 18.0)
+        rows[k, 0:ny] = 0.04 * a * 4 * yy * (1 - yy)                    # u_left x
+        rows[k, ny:2 * ny] = 0.002 * a * rng.standard_normal(ny)        # u_left y
+        if not pressure:
+            rows[k, 2 * ny:3 * ny] = 0.03 * a * 4 * yy * (1 - yy)       # u_right x
+        rows[k, 3 * ny:4 * ny] = 0.001 * a * rng.standard_normal(ny)    # u_right y
+        rows[k, 4 * ny:4 * ny + nx] = 0.08 * a                          # u_top x
+        rows[k, 4 * ny + nx:4 * ny + 2 * nx] = 0.001 * rng.standard_normal(nx)
+        rows[k, 4 * ny + 2 * nx:4 * ny + 3 * nx] = 0.01 * a * rng.standard_normal(nx)
+        rows[k, 4 * ny + 4 * nx:] = 1.0 + 0.01 * rng.standard_normal(ny)
+    return rows
+
+
+def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False):
+    from lbm_b200.solver import Solver
+    s = Solver(nx, ny, tau=0.58, arith=arith, dtype=dtype, right_wall=right)
+    s.set_temporal_blocking(temporal)
+    rng = np.random.default_rng(3)
+    g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
+         * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
+    s.set_populations(g)
+    s.set_walls(_rows(nx, ny, n, 5, right == "pressure"))
+    s.step(1)
+    l0 = s.launches
+    s.step(n, 0, 1, macro_last=macro_last)
+    launches = s.launches - l0
+    out = s.populations("post_collision")
+    mac = s.macro() if macro_last else None
+    s.close()
+    return out, launches, mac
+
+
+@pytest.mark.parametrize("nx,ny", [(17, 70), (33, 64), (50, 130), (128, 128), (4, 5)])
+@pytest.mark.parametrize("right", ["velocity", "pressure"])
+def test_two_update_launch_equals_two_single_updates(nx, ny, right):
+    n = 7
+    a, la, _ = _run(nx, ny, n, True, right)
+    b, lb, _ = _run(nx, ny, n, False, right)
+    assert lb == n and la < n                   # pairs really went through step2_kernel
+    assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
+
+
+@pytest.mark.parametrize("n", [6, 7])
+def test_macro_on_the_last_update(n):
+    a, _, ma = _run(40, 48, n, True, "velocity", macro_last=True)
+    b, _, mb = _run(40, 48, n, False, "velocity", macro_last=True)
+    assert np.array_equal(a, b)
+    assert np.array_equal(ma[0], mb[0]) and np.array_equal(ma[1], mb[1])
+
+
+def test_fused_and_f32_variants_agree_too():
+    for kw in (dict(arith="fused"), dict(arith="fused", dtype="f32"), dict(arith="strict", dtype="f32")):
+        a, _, _ = _run(37, 90, 8, True, "pressure", **kw)
+        b, _, _ = _run(37, 90, 8, False, "pressure", **kw)
+        assert np.array_equal(a, b), kw
+
+
+def test_batched_cavity_against_oracle_bitwise():
+    """Cavity through the batched driver (pairs of updates per launch) == oracle, strict arithmetic."""
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+    cg, co = cases.Cavity(L_lbm=48, sigma=25), cases.Cavity(L_lbm=48, sigma=25)
+    cg.it_max = co.it_max = 201
+    lg = lattice(cg, make_dirs=False, arith="strict")
+    run(lg, cg, batch=64, quiet=True)
+    lo = orc.OracleLattice(co)
+    orc.run_loop(lo, co)
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lg, k), getattr(lo, k)), k

@@ -42,6 +42,45 @@ def _pull_interior(F):
     return G
 
 
+def _worker2(rank, world, port, nx, ny, out):
+    """Depth-2 exchange: after it, two consecutive pulls of the owned columns (the first one also on
+    the one-column rim, as step2_kernel does) equal two pulls of the undivided lattice."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    F = rng.standard_normal((9, nx, ny))
+    x0, nxl = slab.slab_bounds(nx, world, rank)
+    H, pitch = 2, ny + 5
+    view = torch.full((9, nxl + 2 * H, pitch), float("nan"), dtype=torch.float64)
+    view[:, H:nxl + H, :ny] = torch.from_numpy(F[:, x0:x0 + nxl])
+    slab.exchange_halos(view, nxl, rank, world, dist, halo=H, depth=2)
+    local = view.numpy()[:, :, :ny]
+    G2 = _pull_interior(_pull_interior(local))[:, H:nxl + H]
+    ref = _pull_interior(_pull_interior(F))[:, x0:x0 + nxl]
+    ok = True
+    for x in range(nxl):
+        gx = x0 + x
+        for k in range(9):
+            if 0 <= gx - 2 * CX[k] < nx:
+                ok &= np.array_equal(G2[k, x, 2:ny - 2], ref[k, x, 2:ny - 2])
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nx", [(2, 12), (3, 13)])
+def test_depth2_exchange_feeds_two_updates(world, nx):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker2, args=(world, port, nx, 11, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world)) and len(out) == world
+
+
 def _worker(rank, world, port, nx, ny, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -52,7 +91,7 @@ def _worker(rank, world, port, nx, ny, out):
     pitch = ny + 3                                           # padded lines, like the device layout
     view = torch.full((9, nxl + 2, pitch), float("nan"), dtype=torch.float64)
     view[:, 1:nxl + 1, :ny] = torch.from_numpy(F[:, x0:x0 + nxl])
-    slab.exchange_halos(view, nxl, rank, world, dist)
+    slab.exchange_halos(view, nxl, rank, world, dist, halo=1, depth=1)
     local = view.numpy()[:, :, :ny]
     G = _pull_interior(local)[:, 1:nxl + 1]                  # owned columns
     ref = _pull_interior(F)[:, x0:x0 + nxl]

@@ -4,8 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from lbm_b200.solver import Solver
 
-def run(nx, ny, steps, dtype="f64", arith="fused"):
+def run(nx, ny, steps, dtype="f64", arith="fused", temporal=True):
     s = Solver(nx, ny, tau=0.56, dtype=dtype, arith=arith)
+    s.set_temporal_blocking(temporal)
     s.init_equilibrium(1.0)
     s.set_walls(s.wall_row(u_top=np.stack([np.full(nx, 0.1), np.zeros(nx)])))
     s.step(3)
@@ -14,12 +15,11 @@ def run(nx, ny, steps, dtype="f64", arith="fused"):
     ms = s.last_step_ms()
     mlups = nx * ny * steps / (ms * 1e-3) / 1e6
     bpl = 144 if dtype == "f64" else 72
-    print("%6d x %6d %s %s: %8.3f ms/step %9.1f MLUPS %7.1f GB/s" % (nx, ny, dtype, arith, ms / steps, mlups, mlups * bpl / 1e3), flush=True)
+    print("%6d x %6d %s %s tb=%d: %8.3f ms/step %9.1f MLUPS %7.1f GB/s" % (nx, ny, dtype, arith, temporal, ms / steps, mlups, mlups * bpl / 1e3), flush=True)
     s.close()
 
 if __name__ == "__main__":
-    for (nx, ny, st) in ((200, 200, 2000), (1073, 200, 2000), (4096, 4096, 50), (16384, 16384, 10), (32768, 32768, 5)):
+    for (nx, ny, st) in ((200, 200, 2000), (1073, 200, 2000), (4096, 4096, 50), (16384, 16384, 10), (32768, 32768, 6)):
         for dt in ("f64", "f32"):
-            for ar in ("fused", "strict"):
-                if nx >= 16384 and ar == "strict": continue
-                run(nx, ny, st, dt, ar)
+            for tb in (False, True):
+                run(nx, ny, st, dt, "fused", tb)
