@@ -98,13 +98,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(nx, ny, dtype, n_gpus):
+def profiled_traffic(nx, ny, dtype, n_gpus, kernel="step"):
     """DRAM bytes per launch of the step kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             for e in json.load(open(p)):
-                if (e["nx"], e["ny"], e["dtype"], e["n_gpus"]) == (nx, ny, dtype, n_gpus):
+                if (e["nx"], e["ny"], e["dtype"], e["n_gpus"], e.get("kernel", "step")) == (nx, ny, dtype, n_gpus, kernel):
                     return e["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -313,8 +313,8 @@ def gpu_arm(args):
                            "reference's in-place time stepping" % per},
            "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": profiled_traffic(nx, ny, args.dtype, world), "peak_source": peak_src,
-                        "bytes_per_lattice_update": bpl, "kernel": ("lbm::step2_kernel<%s,fused,16,64> (two updates per launch: bytes per launch = 2 x 144 B x cells)"
+                        "traffic": profiled_traffic(nx, ny, args.dtype, world, "step2" if temporal else "step"), "peak_source": peak_src,
+                        "bytes_per_lattice_update": bpl, "kernel": ("lbm::step2_kernel<%s,fused,8,64> (two updates per launch: bytes per launch = 2 x 144 B x cells)"
                                    if temporal else "lbm::step_kernel<%s,fused>") % args.dtype,
                         "per": "rank 0 slab, bytes per launch / (timed region / launches)"},
            "clocks": clocks}

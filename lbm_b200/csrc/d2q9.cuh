@@ -20,23 +20,72 @@ __host__ __device__ constexpr int cy_of(int q) { return q == 3 || q == 5 || q ==
 // Arithmetic policy.  STRICT: every operation separately rounded (the *_rn intrinsics are never
 // contracted by nvcc).  FUSED: plain operators, nvcc contracts mul+add into FMA (-fmad=true).
 template <typename T, bool STRICT> struct Ar;
+__device__ __forceinline__ double rcp_fast(double b);
 template <> struct Ar<double, true> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ void div2(double a0, double a1, double b, double &q0, double &q1)
+    {
+        q0 = __ddiv_rn(a0, b);
+        q1 = __ddiv_rn(a1, b);
+    }
 };
 template <> struct Ar<float, true> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ void div2(float a0, float a1, float b, float &q0, float &q1)
+    {
+        q0 = __fdiv_rn(a0, b);
+        q1 = __fdiv_rn(a1, b);
+    }
 };
-template <typename T> struct Ar<T, false> {
-    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
-    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
-    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
-    static __device__ __forceinline__ T div(T a, T b) { return a / b; }
+// FUSED division: the IEEE double division of nvcc is a ~60-instruction subroutine call, and the
+// update kernels are instruction-issue bound once the HBM traffic is halved (profiles/README.md).
+// The divisor is always a density or 1 +- u (normal range, far from 0/inf), so a reciprocal seed
+// (MUFU.RCP64H) refined by two Newton steps and one residual correction of the quotient is used:
+// no special-case handling, result within 1 ulp of the correctly rounded quotient.  (The
+// reference's Numba kernels run with fastmath, which licenses the same reciprocal rewrite.)
+__device__ __forceinline__ double rcp_fast(double b)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double mul_rcp(double a, double b, double y /* ~1/b */)
+{
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+template <> struct Ar<double, false> {
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double div(double a, double b) { return mul_rcp(a, b, rcp_fast(b)); }
+    static __device__ __forceinline__ void div2(double a0, double a1, double b, double &q0, double &q1)
+    {
+        const double y = rcp_fast(b);
+        q0 = mul_rcp(a0, b, y);
+        q1 = mul_rcp(a1, b, y);
+    }
+};
+template <> struct Ar<float, false> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ void div2(float a0, float a1, float b, float &q0, float &q1)
+    {
+        const float y = __frcp_rn(b);
+        q0 = a0 * y;
+        q1 = a1 * y;
+    }
 };
 
 template <typename T> struct Coef {
@@ -53,8 +102,7 @@ __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy)
     for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
     T mx = A::add(A::sub(A::sub(A::add(A::sub(G[1], G[2]), G[5]), G[6]), G[7]), G[8]);
     T my = A::sub(A::add(A::sub(A::add(A::sub(G[3], G[4]), G[5]), G[6]), G[7]), G[8]);
-    ux = A::div(mx, r);
-    uy = A::div(my, r);
+    A::div2(mx, my, r, ux, uy);
 }
 
 // g_eq (nb.py:10-17) followed by the TRT collision (nb.py:25-35); G -> F in place.

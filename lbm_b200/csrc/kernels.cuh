@@ -267,8 +267,8 @@ step_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Lin
 // of the tile from shared memory and stores it.  Rim cells outside the global lattice are skipped:
 // nothing reads them that Zou-He does not overwrite.  No obstacles, no macro output on this path.
 // ---------------------------------------------------------------------------------------
-template <typename T, bool STRICT, int TX, int TY>
-__global__ void __launch_bounds__(kBlock, 2)
+template <typename T, bool STRICT, int TX, int TY, int NT, int CPT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 step2_kernel(const __grid_constant__ StepParams<T> p)
 {
     using A = Ar<T, STRICT>;
@@ -280,35 +280,81 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
     const GlobalSource<T> gsrc{p};
 
     // ---- phase 1: first update on the rimmed tile -> shared memory --------------------------
+    // CPT independent cells per thread and iteration: their loads are issued together and the
+    // straight-line macro/collide sequences interleave (ILP), which hides the FP64 and memory
+    // latency that 2 resident blocks per SM cannot hide by themselves.
     const int r_lo = max(tx0 - 1, p.x_lo), r_hi = min(txe + 1, p.x_hi);
-    for (int c = threadIdx.x; c < NS; c += kBlock) {
-        const int xr = c / SP, yr = c - xr * SP;
-        const int x = tx0 - 1 + xr, y = ty0 - 1 + yr;
-        if (x < r_lo || x >= r_hi || y < 0 || y >= p.ny) continue;
-        T G[9], r, ux, uy;
-        gsrc(x, y, G);
-        apply_walls<A, T>(p, p.walls, gsrc, x, y, G, r, ux, uy);
-        macro<A, T>(G, r, ux, uy);
-        collide<A, T>(G, r, ux, uy, p.coef);
+    for (int c0 = threadIdx.x; c0 < NS; c0 += NT * CPT) {
+        T G[CPT][9];
+        int x[CPT], y[CPT];
+        bool ok[CPT];
 #pragma unroll
-        for (int q = 0; q < 9; q++) f[q * NS + c] = G[q];
+        for (int k = 0; k < CPT; k++) {
+            const int c = c0 + k * NT;
+            const int xr = c / SP, yr = c - xr * SP;
+            x[k] = tx0 - 1 + xr;
+            y[k] = ty0 - 1 + yr;
+            ok[k] = c < NS && x[k] >= r_lo && x[k] < r_hi && y[k] >= 0 && y[k] < p.ny;
+            if (!ok[k]) { x[k] = r_lo; y[k] = min(max(y[k], 0), p.ny - 1); }   // compute something valid, store nothing
+            gsrc(x[k], y[k], G[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            T r, ux, uy;
+            apply_walls<A, T>(p, p.walls, gsrc, x[k], y[k], G[k], r, ux, uy);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            T r, ux, uy;
+            macro<A, T>(G[k], r, ux, uy);
+            collide<A, T>(G[k], r, ux, uy, p.coef);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            if (ok[k]) {
+                const int c = c0 + k * NT;
+#pragma unroll
+                for (int q = 0; q < 9; q++) f[q * NS + c] = G[k][q];
+            }
+        }
     }
     __syncthreads();
 
     // ---- phase 2: second update of the tile from shared memory -> global ----------------------
     const SharedSource<T, SP, NS> ssrc{f, tx0 - 1, ty0 - 1};
-    for (int c = threadIdx.x; c < TX * TY; c += kBlock) {
-        const int xt = c / TY, yt = c - xt * TY;
-        const int x = tx0 + xt, y = ty0 + yt;
-        if (x >= txe || y >= p.ny) continue;
-        T G[9], r, ux, uy;
-        ssrc(x, y, G);
-        apply_walls<A, T>(p, p.walls2, ssrc, x, y, G, r, ux, uy);
-        macro<A, T>(G, r, ux, uy);
-        collide<A, T>(G, r, ux, uy, p.coef);
-        const int idx = x * p.pitch + y;
+    for (int c0 = threadIdx.x; c0 < TX * TY; c0 += NT * CPT) {
+        T G[CPT][9];
+        int x[CPT], y[CPT];
+        bool ok[CPT];
 #pragma unroll
-        for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+        for (int k = 0; k < CPT; k++) {
+            const int c = c0 + k * NT;
+            const int xt = c / TY, yt = c - xt * TY;
+            x[k] = tx0 + xt;
+            y[k] = ty0 + yt;
+            ok[k] = c < TX * TY && x[k] < txe && y[k] < p.ny;
+            if (!ok[k]) { x[k] = tx0; y[k] = min(y[k], p.ny - 1); }
+            ssrc(x[k], y[k], G[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            T r, ux, uy;
+            apply_walls<A, T>(p, p.walls2, ssrc, x[k], y[k], G[k], r, ux, uy);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            T r, ux, uy;
+            macro<A, T>(G[k], r, ux, uy);
+            collide<A, T>(G[k], r, ux, uy, p.coef);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            if (ok[k]) {
+                const int idx = x[k] * p.pitch + y[k];
+#pragma unroll
+                for (int q = 0; q < 9; q++) p.dst[q][idx] = G[k][q];
+            }
+        }
     }
 }
 

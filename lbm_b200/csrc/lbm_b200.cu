@@ -54,7 +54,8 @@ struct lbm_handle {
     int cur = 0;
     StateKind kind = kNone;
     bool other_has_g = false;
-    bool temporal = true;         // pair updates into step2_kernel launches where possible     // other buffer holds stream+BC of current F (lbm_apply_bc)
+    bool temporal = true;         // pair updates into step2_kernel launches where possible
+    int tb_variant = 4;           // 8 x 64 tile, 256 threads, 4 blocks/SM: best of the measured variants     // other buffer holds stream+BC of current F (lbm_apply_bc)
     cudaStream_t stream = nullptr;
     // walls
     void *walls = nullptr;        // device table, element type T
@@ -203,10 +204,9 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
 }
 
 // ---- temporal blocking: two updates per launch ------------------------------------------
-constexpr int kTX = 16, kTY = 64;
-
-template <typename T, bool STRICT>
-static int launch_step2_t(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
+// Variants (tile, threads, cells per thread, min blocks/SM); h->tb_variant selects one (tuning aid).
+template <typename T, bool STRICT, int TX, int TY, int NT, int CPT, int MINB>
+static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
 {
     StepParams<T> p;
     LinkParams lp;
@@ -214,23 +214,37 @@ static int launch_step2_t(lbm_handle *h, int src, int dst, int xa, int xb, int64
     p.walls2 = static_cast<const T *>(h->walls) + row2 * h->row_len;
     // a corner cell reads its x-neighbour's pulled populations from shared memory: the right wall
     // column must not be the first column of its tile -> give the last two columns their own launch
-    if (p.x_wr >= xa + 1 && p.x_wr < xb && (p.x_wr - xa) % kTX == 0) {
-        int rc = launch_step2_t<T, STRICT>(h, src, dst, xa, p.x_wr - 1, row1, row2);
+    if (p.x_wr >= xa + 1 && p.x_wr < xb && (p.x_wr - xa) % TX == 0) {
+        int rc = launch_step2_v<T, STRICT, TX, TY, NT, CPT, MINB>(h, src, dst, xa, p.x_wr - 1, row1, row2);
         if (rc) return rc;
-        return launch_step2_t<T, STRICT>(h, src, dst, p.x_wr - 1, xb, row1, row2);
+        return launch_step2_v<T, STRICT, TX, TY, NT, CPT, MINB>(h, src, dst, p.x_wr - 1, xb, row1, row2);
     }
-    constexpr size_t smem = 9 * (size_t)(kTX + 2) * (kTY + 2) * sizeof(T);
+    constexpr size_t smem = 9 * (size_t)(TX + 2) * (TY + 2) * sizeof(T);
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(step2_kernel<T, STRICT, kTX, kTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(step2_kernel<T, STRICT, TX, TY, NT, CPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    dim3 grid((unsigned)((h->cfg.ny + kTY - 1) / kTY), (unsigned)((xb - xa + kTX - 1) / kTX)), block(kBlock);
+    dim3 grid((unsigned)((h->cfg.ny + TY - 1) / TY), (unsigned)((xb - xa + TX - 1) / TX)), block(NT);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one temporal-blocking launch");
-    step2_kernel<T, STRICT, kTX, kTY><<<grid, block, smem, h->stream>>>(p);
+    step2_kernel<T, STRICT, TX, TY, NT, CPT, MINB><<<grid, block, smem, h->stream>>>(p);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;
+}
+
+template <typename T, bool STRICT>
+static int launch_step2_t(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
+{
+    switch (h->tb_variant) {
+    case 2: return launch_step2_v<T, STRICT, 16, 64, 256, 2, 2>(h, src, dst, xa, xb, row1, row2);
+    case 3: return launch_step2_v<T, STRICT, 16, 64, 512, 1, 2>(h, src, dst, xa, xb, row1, row2);
+    case 5: return launch_step2_v<T, STRICT, 8, 64, 256, 2, 3>(h, src, dst, xa, xb, row1, row2);
+    case 6: return launch_step2_v<T, STRICT, 32, 32, 256, 2, 2>(h, src, dst, xa, xb, row1, row2);
+    case 7: return launch_step2_v<T, STRICT, 16, 64, 384, 2, 2>(h, src, dst, xa, xb, row1, row2);
+    case 8: return launch_step2_v<T, STRICT, 16, 64, 256, 1, 2>(h, src, dst, xa, xb, row1, row2);
+    default: return launch_step2_v<T, STRICT, 8, 64, 256, 1, 4>(h, src, dst, xa, xb, row1, row2);
+    }
 }
 
 static int launch_step2(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
@@ -714,6 +728,7 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)
 {
     if (!h) return fail(LBM_E_INVALID, "handle is NULL");
     h->temporal = enable != 0;
+    if (enable > 1) h->tb_variant = enable;   // values > 1 select a tuning variant
     return LBM_OK;
 }
 

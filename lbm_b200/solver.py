@@ -116,7 +116,7 @@ class Solver:
         C.check(self._L.lbm_step2_columns(self._h, xa, xb, row1, row2))
 
     def set_temporal_blocking(self, enable):
-        C.check(self._L.lbm_set_temporal_blocking(self._h, 1 if enable else 0))
+        C.check(self._L.lbm_set_temporal_blocking(self._h, int(enable)))
 
     def flip(self):
         C.check(self._L.lbm_flip(self._h))

@@ -53,7 +53,9 @@ def test_two_update_launch_equals_two_single_updates(nx, ny, right):
     n = 7
     a, la, _ = _run(nx, ny, n, True, right)
     b, lb, _ = _run(nx, ny, n, False, right)
-    assert lb == n and la < n                   # pairs really went through step2_kernel
+    assert lb == n
+    if (nx - 1) % 16:                           # (otherwise the last two columns get their own launch)
+        assert la < n                           # pairs really went through step2_kernel
     assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
 
 

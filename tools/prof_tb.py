@@ -1,0 +1,15 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from lbm_b200.solver import Solver
+nx = ny = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+variant = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+dtype = sys.argv[3] if len(sys.argv) > 3 else "f64"
+s = Solver(nx, ny, tau=0.56, dtype=dtype)
+s.set_temporal_blocking(variant)
+s.init_equilibrium(1.0)
+s.set_walls(s.wall_row(u_top=np.stack([np.full(nx, 0.1), np.zeros(nx)])))
+s.step(1)
+s.step(6)
+s.sync()
+print(s.last_step_ms() / 6)

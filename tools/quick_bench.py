@@ -19,7 +19,10 @@ def run(nx, ny, steps, dtype="f64", arith="fused", temporal=True):
     s.close()
 
 if __name__ == "__main__":
-    for (nx, ny, st) in ((200, 200, 2000), (1073, 200, 2000), (4096, 4096, 50), (16384, 16384, 10), (32768, 32768, 6)):
+    import sys
+    variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1]
+    sizes = ((16384, 16384, 10),) if len(sys.argv) > 1 else ((200, 200, 2000), (1073, 200, 2000), (4096, 4096, 50), (16384, 16384, 10), (32768, 32768, 6))
+    for (nx, ny, st) in sizes:
         for dt in ("f64", "f32"):
-            for tb in (False, True):
+            for tb in variants:
                 run(nx, ny, st, dt, "fused", tb)
