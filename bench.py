@@ -294,7 +294,10 @@ def gpu_arm(args):
     h2d = int(sum_over_ranks(row_len * 8 * per))
     d2h = int(sum_over_ranks(d2h))
 
-    bpl = BYTES_PER_LUP[args.dtype]
+    # algorithmic bytes: one read + one write of the nine populations per cell and LAUNCH; a
+    # two-update launch (temporal blocking) serves two lattice updates with them.
+    upl = 2 if (temporal and K >= 2) else 1
+    bpl = BYTES_PER_LUP[args.dtype] / upl
     peak, peak_src = measured_peak()
     achieved = bpl * s.nxl * ny / (ms / K * 1e-3) / 1e9      # this rank's kernel: bytes per launch / duration
     out = {"metric": "MLUPS (%s)" % args.dtype, "value": value, "unit": "MLUPS", "n_gpus": world,
@@ -314,7 +317,8 @@ def gpu_arm(args):
            "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": profiled_traffic(nx, ny, args.dtype, world, "step2" if temporal else "step"), "peak_source": peak_src,
-                        "bytes_per_lattice_update": bpl, "kernel": ("lbm::step2_kernel<%s,fused,8,64> (two updates per launch: bytes per launch = 2 x 144 B x cells)"
+                        "bytes_per_lattice_update": bpl, "updates_per_launch": upl,
+                        "bytes_per_launch": BYTES_PER_LUP[args.dtype] * s.nxl * ny, "kernel": ("lbm::step2_kernel<%s,fused,8,64> (two updates per launch; the populations cross HBM once per launch)"
                                    if temporal else "lbm::step_kernel<%s,fused>") % args.dtype,
                         "per": "rank 0 slab, bytes per launch / (timed region / launches)"},
            "clocks": clocks}
