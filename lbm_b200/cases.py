@@ -23,6 +23,50 @@ _GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
                        "tests", "golden")
 
 
+class ConvergenceBuffer:
+    """Triple moving average of an observable with the growth-rate convergence flag of the
+    reference's buff class (/root/reference/lbm/src/utils/buff.py:8-77), same arithmetic on the
+    same slices (np.sum is NumPy's pairwise sum in both), but on geometrically grown arrays instead
+    of one np.append reallocation per value and level."""
+
+    def __init__(self, name, dt, obs_cv_ct, obs_cv_nb, output_dir=None):
+        self.name, self.dt = name, dt
+        self.obs_cv_ct, self.obs_cv_nb = obs_cv_ct, obs_cv_nb
+        self.it, self.obs, self.obs_cv_cnt, self.obs_cv = 0, 0.0, 0, False
+        self._n = 2                                   # every level starts as [0, 0] (buff.py:18-21)
+        self._lv = [np.zeros(1024) for _ in range(4)]  # raw values, avg1, avg2, avg3
+
+    def _grow(self):
+        if self._n + 1 > len(self._lv[0]):
+            self._lv = [np.concatenate([a, np.zeros(len(a))]) for a in self._lv]
+
+    def add(self, value):                             # buff.py:35-38
+        self._grow()
+        self._lv[0][self._n] = value
+        self.it += 1
+
+    def mv_avg(self):                                 # buff.py:51-77
+        it_s, it_e = math.floor(self.it * 4 / 5), self.it
+        n = self._n
+        cnt = float(it_e - it_s + 1)
+        self.obs = np.sum(self._lv[0][it_s:it_e]) / cnt
+        for lv in (1, 2, 3):
+            self._lv[lv][n] = self.obs
+            self.obs = np.sum(self._lv[lv][it_s:it_e]) / cnt
+        self._n = n + 1
+        growth = 0.0
+        if self.it > 10:
+            a3 = self._lv[3]
+            growth = (a3[it_e] - a3[it_s]) / ((it_e - it_s + 1) * self.dt)
+            if abs(growth) < self.obs_cv_ct:
+                self.obs_cv_cnt += 1
+            else:
+                self.obs_cv_cnt = 0
+            if self.obs_cv_cnt > self.obs_cv_nb:
+                self.obs_cv = True
+        return self.obs, growth
+
+
 class Obstacle:
     """Link list of one body: rows (i, j, q) with q pointing fluid -> solid and the
     IBB wall distance of each link (obstacle.py:3-25, produced by lattice.py:290-375)."""
@@ -162,8 +206,24 @@ class Channel(Case):
 
     def observables(self, lattice, it):
         if self.obstacles and getattr(self, "track_forces", False):
-            self.forces.append(lattice.drag_lift(self.obstacles[0], self.rho_lbm, self.u_avg,
-                                                 self.D_lbm))
+            cx, cy = lattice.drag_lift(self.obstacles[0], self.rho_lbm, self.u_avg, self.D_lbm)
+            self.forces.append((cx, cy))
+            if self.stop == "obs":                   # turek.add_buff, turek.py:147-155
+                self.drag_buff.add(cx)
+                self.lift_buff.add(cy)
+                self.avg_drag, _ = self.drag_buff.mv_avg()
+                self.avg_lift, _ = self.lift_buff.mv_avg()
+
+    def check_stop(self, it):
+        if self.stop == "obs":                       # base_app.py:63-67
+            return not (self.drag_buff.obs_cv and self.lift_buff.obs_cv)
+        return it < self.it_max
+
+    def initialize(self, lattice):
+        if self.stop == "obs":                       # turek.py:77-87
+            self.drag_buff = ConvergenceBuffer("drag", lattice.dt, lattice.obs_cv_ct, lattice.obs_cv_nb)
+            self.lift_buff = ConvergenceBuffer("lift", lattice.dt, lattice.obs_cv_ct, lattice.obs_cv_nb)
+        super().initialize(lattice)
 
 
 class Poiseuille(Channel):
@@ -191,8 +251,12 @@ class Turek(Channel):
     IBB = True
     track_forces = True
 
-    def __init__(self, L_lbm=100, Re_lbm=20.0, u_lbm=0.05, sigma=None, links=None):
+    obs_cv_ct = 1.0e-3      # turek.py:27-29
+    obs_cv_nb = 1000
+
+    def __init__(self, L_lbm=100, Re_lbm=20.0, u_lbm=0.05, sigma=None, links=None, stop="it"):
         super().__init__()
+        self.stop = stop
         self.L_lbm, self.Re_lbm, self.u_lbm, self.t_max = L_lbm, Re_lbm, u_lbm, 0.02
         self.x_min, self.x_max, self.y_min, self.y_max = -0.2, 2.0, -0.2, 0.21
         self.ny = L_lbm

@@ -55,6 +55,7 @@ struct lbm_handle {
     StateKind kind = kNone;
     bool other_has_g = false;
     bool temporal = true;         // pair updates into step2_kernel launches where possible
+    int pf_ahead = 0;
     int tb_variant = 4;           // 8 x 64 tile, 256 threads, 4 blocks/SM: best of the measured variants     // other buffer holds stream+BC of current F (lbm_apply_bc)
     cudaStream_t stream = nullptr;
     // walls
@@ -190,6 +191,7 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.mask = h->d_mask;
     p.right_pressure = h->cfg.right_wall == LBM_RIGHT_PRESSURE;
     p.write_macro = 0;
+    p.pf_ahead = h->pf_ahead;
     lp.n_cells = h->n_cells;
     lp.n_links = h->n_links;
     lp.n_obs = h->n_obs;
@@ -728,7 +730,8 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)
 {
     if (!h) return fail(LBM_E_INVALID, "handle is NULL");
     h->temporal = enable != 0;
-    if (enable > 1) h->tb_variant = enable;   // values > 1 select a tuning variant
+    if (enable > 1) h->tb_variant = enable % 100;   // values > 1 select a tuning variant
+    h->pf_ahead = (enable / 100) * 148;         // hundreds digit: L2 prefetch distance in units of 148 blocks
     return LBM_OK;
 }
 

@@ -174,8 +174,25 @@ def run_fixture(ns, name, app, n_iters, forces):
     print(name, lat.nx, lat.ny, "iters", n_iters, "max|u|", float(np.abs(lat.u).max()))
 
 
+def buff_fixture(ns):
+    """buff.add / buff.mv_avg (lbm/src/utils/buff.py) on a seeded, converging series."""
+    rng = np.random.default_rng(5)
+    b = ns.buff.buff("drag", 0.004, 1.0e-2, 200, "./")
+    n = 2500
+    x = -5.7 + 2.0 * np.exp(-np.arange(n) / 120.0) + 1e-4 * rng.standard_normal(n) * np.exp(-np.arange(n) / 400.0)
+    obs, growth, flag = np.zeros(n), np.zeros(n), np.zeros(n, dtype=bool)
+    for k in range(n):
+        b.add(x[k])
+        obs[k], growth[k] = b.mv_avg()
+        flag[k] = b.obs_cv
+    np.savez_compressed(os.path.join(HERE, "buff.npz"), x=x, obs=obs, growth=growth, flag=flag,
+                        dt=0.004, ct=1.0e-2, nb=200)
+    print("buff: first converged at", int(np.argmax(flag)) if flag.any() else None)
+
+
 def main():
     ns = refload.load()
+    buff_fixture(ns)
     A = ns.app.app_factory.create
     # --- link lists of the BASELINE configs 2, 3, 4 -------------------------
     for name, L in (("turek100", 100), ("turek200", 200)):

@@ -163,3 +163,14 @@ def test_reference_known_answer_cavity():
     assert abs(vx[50] - 0.05295104908939561) < 1.0e-6
     assert abs(uy[10] + 0.05968571489630510) < 1.0e-6
     assert abs(uy[50] + 0.19792323493599165) < 1.0e-6
+
+
+def test_convergence_buffer_matches_reference_buff():
+    """cases.ConvergenceBuffer == lbm/src/utils/buff.py on a stored series (values, growth, flag)."""
+    z = np.load(os.path.join(GOLDEN, "buff.npz"))
+    b = cases.ConvergenceBuffer("drag", float(z["dt"]), float(z["ct"]), int(z["nb"]))
+    for k, v in enumerate(z["x"]):
+        b.add(v)
+        obs, growth = b.mv_avg()
+        assert obs == z["obs"][k] and growth == z["growth"][k] and b.obs_cv == bool(z["flag"][k]), k
+    assert z["flag"].any()
