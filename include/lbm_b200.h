@@ -149,8 +149,9 @@ int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot
 int lbm_flip(lbm_t *h);
 /* Two consecutive updates (wall rows row1, row2) of local columns [xa, xb) in ONE launch
  * (temporal blocking through shared memory), without flipping; reads columns xa-2 .. xb+1.
- * Not available with obstacle links.  lbm_step pairs updates this way by itself unless
- * lbm_set_temporal_blocking(h, 0) was called. */
+ * Not available with obstacle links.  lbm_step pairs updates this way by itself when the lattice
+ * has no obstacles and is large enough to profit (>= 1184 tiles of 8 x 64 cells), unless
+ * lbm_set_temporal_blocking(h, 0) was called; enable < 0 forces pairing on any size (tests). */
 int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2);
 int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
 

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,10 +54,11 @@ struct lbm_handle {
     bool own_buf = false;
     int cur = 0;
     StateKind kind = kNone;
-    bool other_has_g = false;
+    bool other_has_g = false;     // other buffer holds stream+BC of current F (lbm_apply_bc)
     bool temporal = true;         // pair updates into step2_kernel launches where possible
-    int pf_ahead = 0;
-    int tb_variant = 4;           // 8 x 64 tile, 256 threads, 4 blocks/SM: best of the measured variants     // other buffer holds stream+BC of current F (lbm_apply_bc)
+    int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
+    bool tb_force = false;        // pair updates even on small lattices (tests)
+    bool smem_attr_set = false;
     cudaStream_t stream = nullptr;
     // walls
     void *walls = nullptr;        // device table, element type T
@@ -206,7 +208,6 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
 }
 
 // ---- temporal blocking: two updates per launch ------------------------------------------
-// Variants (tile, threads, cells per thread, min blocks/SM); h->tb_variant selects one (tuning aid).
 template <typename T, bool STRICT, int TX, int TY, int NT, int CPT, int MINB>
 static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
 {
@@ -222,10 +223,9 @@ static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64
         return launch_step2_v<T, STRICT, TX, TY, NT, CPT, MINB>(h, src, dst, p.x_wr - 1, xb, row1, row2);
     }
     constexpr size_t smem = 9 * (size_t)(TX + 2) * (TY + 2) * sizeof(T);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!h->smem_attr_set) {   // per handle: the attribute belongs to the handle's device
         CUDA_TRY(cudaFuncSetAttribute(step2_kernel<T, STRICT, TX, TY, NT, CPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        h->smem_attr_set = true;
     }
     dim3 grid((unsigned)((h->cfg.ny + TY - 1) / TY), (unsigned)((xb - xa + TX - 1) / TX)), block(NT);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one temporal-blocking launch");
@@ -238,15 +238,10 @@ static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64
 template <typename T, bool STRICT>
 static int launch_step2_t(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
 {
-    switch (h->tb_variant) {
-    case 2: return launch_step2_v<T, STRICT, 16, 64, 256, 2, 2>(h, src, dst, xa, xb, row1, row2);
-    case 3: return launch_step2_v<T, STRICT, 16, 64, 512, 1, 2>(h, src, dst, xa, xb, row1, row2);
-    case 5: return launch_step2_v<T, STRICT, 8, 64, 256, 2, 3>(h, src, dst, xa, xb, row1, row2);
-    case 6: return launch_step2_v<T, STRICT, 32, 32, 256, 2, 2>(h, src, dst, xa, xb, row1, row2);
-    case 7: return launch_step2_v<T, STRICT, 16, 64, 384, 2, 2>(h, src, dst, xa, xb, row1, row2);
-    case 8: return launch_step2_v<T, STRICT, 16, 64, 256, 1, 2>(h, src, dst, xa, xb, row1, row2);
-    default: return launch_step2_v<T, STRICT, 8, 64, 256, 1, 4>(h, src, dst, xa, xb, row1, row2);
-    }
+    // Tile / block shape chosen by measurement on B200 at 16384^2 (profiles/README.md): 8 x 64 cells,
+    // 256 threads, 4 blocks per SM (<= 64 registers) beat 16x64, 32x32, 16x32, 12x32, 8x32 tiles,
+    // 384/512-thread blocks, two cells per thread, and a persistent cp.async-staged variant.
+    return launch_step2_v<T, STRICT, 8, 64, 256, 1, 4>(h, src, dst, xa, xb, row1, row2);
 }
 
 static int launch_step2(lbm_handle *h, int src, int dst, int xa, int xb, int64_t row1, int64_t row2)
@@ -680,7 +675,10 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
         // two updates in one launch when neither needs obstacle links or macro output
         const bool wm_next = (s + 1 == n_updates - 1) && (flags & LBM_STEP_MACRO_LAST);
-        if (h->temporal && mode == kFused && h->n_obs == 0 && s + 1 < n_updates && !wm_next && h->cfg.nxl >= 4) {
+        // ... and the lattice has enough 8 x 64 tiles for two full waves of 4 blocks per SM
+        // (below that the single-update kernel is faster: small lattices are latency bound)
+        const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * 148 || h->tb_force;
+        if (h->temporal && big && mode == kFused && h->n_obs == 0 && s + 1 < n_updates && !wm_next && h->cfg.nxl >= 4) {
             rc = launch_step2(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride,
                               first_row + (s + 1) * row_stride);
             if (rc) return rc;
@@ -730,8 +728,8 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)
 {
     if (!h) return fail(LBM_E_INVALID, "handle is NULL");
     h->temporal = enable != 0;
-    if (enable > 1) h->tb_variant = enable % 100;   // values > 1 select a tuning variant
-    h->pf_ahead = (enable / 100) * 148;         // hundreds digit: L2 prefetch distance in units of 148 blocks
+    h->tb_force = enable < 0;                   // negative: also on lattices too small to profit (tests)
+    if (enable < 0) enable = -enable;
     return LBM_OK;
 }
 

@@ -31,7 +31,7 @@ def _rows(nx, ny, n, seed, pressure):
 def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False):
     from lbm_b200.solver import Solver
     s = Solver(nx, ny, tau=0.58, arith=arith, dtype=dtype, right_wall=right)
-    s.set_temporal_blocking(temporal)
+    s.set_temporal_blocking(-1 if temporal else 0)
     rng = np.random.default_rng(3)
     g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
          * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
@@ -81,6 +81,9 @@ def test_batched_cavity_against_oracle_bitwise():
     cg, co = cases.Cavity(L_lbm=48, sigma=25), cases.Cavity(L_lbm=48, sigma=25)
     cg.it_max = co.it_max = 201
     lg = lattice(cg, make_dirs=False, arith="strict")
+    lg._handle()
+    from lbm_b200 import _capi
+    _capi.check(lg._L.lbm_set_temporal_blocking(lg._h, -1))
     run(lg, cg, batch=64, quiet=True)
     lo = orc.OracleLattice(co)
     orc.run_loop(lo, co)

@@ -6,7 +6,7 @@ from lbm_b200.solver import Solver
 
 def run(nx, ny, steps, dtype="f64", arith="fused", temporal=True):
     s = Solver(nx, ny, tau=0.56, dtype=dtype, arith=arith)
-    s.set_temporal_blocking(temporal)
+    s.set_temporal_blocking(-1 if temporal else 0)
     s.init_equilibrium(1.0)
     s.set_walls(s.wall_row(u_top=np.stack([np.full(nx, 0.1), np.zeros(nx)])))
     s.step(3)
