@@ -116,6 +116,10 @@ int lbm_set_right_wall(lbm_t *h, int32_t right_wall);
 
 /* lattice.g = ... (cavity.py:62, turek.py:91): upload pre-collision populations g[9][nxl][ny]. */
 int lbm_set_populations(lbm_t *h, const void *g_host);
+/* Restart: install post-collision populations F[9][nxl][ny] (what lbm_get_populations(...,
+ * LBM_POP_POST_COLLISION, ...) returned) as the current state; the next update is a fused one.
+ * The reference has no checkpoint/restart; its whole state is this array. */
+int lbm_set_post_collision(lbm_t *h, const void *f_host);
 /* Same state without a host array: g_q = equilibrium(rho, ux, uy) everywhere, computed on the
  * device (what the apps' initialize() produces with u = 0: cavity.py:54-62). */
 int lbm_init_equilibrium(lbm_t *h, double rho, double ux, double uy);

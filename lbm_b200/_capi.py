@@ -52,6 +52,7 @@ SIGNATURES = {
     "lbm_sync": (ctypes.c_int, [c_vp]),
     "lbm_set_right_wall": (ctypes.c_int, [c_vp, c_i32]),
     "lbm_set_populations": (ctypes.c_int, [c_vp, c_vp]),
+    "lbm_set_post_collision": (ctypes.c_int, [c_vp, c_vp]),
     "lbm_init_equilibrium": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "lbm_equilibrium": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "lbm_set_links": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32]),

@@ -433,20 +433,24 @@ static int copy_field_d2h(lbm_handle *h, const void *dev_cell0, int64_t dev_plan
     return LBM_OK;
 }
 
-int lbm_set_populations(lbm_t *h, const void *g_host)
+static int upload_populations(lbm_t *h, const void *host, StateKind kind)
 {
     CHECK_H(h);
-    if (!g_host) return fail(LBM_E_INVALID, "g_host is NULL");
+    if (!host) return fail(LBM_E_INVALID, "host array is NULL");
     int rc = ensure_state(h);
     if (rc) return rc;
-    rc = copy_field_h2d(h, elem_ptr(h, h->cur, 0), h->lay.plane, g_host, 9);
+    rc = copy_field_h2d(h, elem_ptr(h, h->cur, 0), h->lay.plane, host, 9);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may free g_host on return
-    h->kind = kHaveG;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may free the host array on return
+    h->kind = kind;
     h->other_has_g = false;
     h->macro_valid = false;
     return LBM_OK;
 }
+
+int lbm_set_populations(lbm_t *h, const void *g_host) { return upload_populations(h, g_host, kHaveG); }
+
+int lbm_set_post_collision(lbm_t *h, const void *f_host) { return upload_populations(h, f_host, kHaveF); }
 
 int lbm_init_equilibrium(lbm_t *h, double rho, double ux, double uy)
 {

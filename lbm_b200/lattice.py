@@ -459,6 +459,31 @@ class lattice:
         C.check(self._L.lbm_forces_now(self._handle(), self._ptr(out)))
         return out
 
+    def save_checkpoint(self, path):
+        """Write the restartable state (post-collision populations, recorded wall profiles, iteration
+        count) to an .npz file.  Valid after a completed set_bc."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "save_checkpoint() must follow set_bc")
+        np.savez(path, F=self.g_up, row=self._row, updates=self.updates, right_wall=self._right_wall,
+                 bcs=np.array(sorted(self._bcs)), dtype=self.dtype)
+
+    def load_checkpoint(self, path):
+        """Restore a state written by save_checkpoint; continue with app.set_inlets / lattice.macro()
+        of the next iteration.  Obstacles are re-recorded by the next set_bc; until then the links
+        uploaded last stay in force, so call this on a lattice that ran the same app."""
+        z = np.load(path)
+        F = np.ascontiguousarray(z["F"], dtype=self._np)
+        if F.shape != (9, self.nx, self.ny):
+            raise ValueError("checkpoint has shape %s, lattice is (9, %d, %d)" % (F.shape, self.nx, self.ny))
+        C.check(self._L.lbm_set_post_collision(self._handle(), self._ptr(F)))
+        self._switch_right(int(z["right_wall"]))
+        self._row[:] = z["row"]
+        self._row_dev = None
+        self._bcs = set(str(b) for b in z["bcs"])
+        self.updates = int(z["updates"])
+        self._state = "streamed"
+        self._cache = {}
+
     def save_state(self):
         """Device-side copy of the current post-collision populations (for exact stop-rule rollback)."""
         cur = C.c_vp()

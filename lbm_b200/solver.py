@@ -67,6 +67,11 @@ class Solver:
         assert g.shape == (9, self.nxl, self.ny)
         C.check(self._L.lbm_set_populations(self._h, self._p(g)))
 
+    def set_post_collision(self, F):
+        F = np.ascontiguousarray(F, dtype=self.np_dtype)
+        assert F.shape == (9, self.nxl, self.ny)
+        C.check(self._L.lbm_set_post_collision(self._h, self._p(F)))
+
     def init_equilibrium(self, rho=1.0, ux=0.0, uy=0.0):
         C.check(self._L.lbm_init_equilibrium(self._h, rho, ux, uy))
 

@@ -90,3 +90,27 @@ def test_outputs_see_the_fields_of_their_iteration():
     vx, uy = cg.line_fields(lg)
     vxo, uyo = co.line_fields(lo)
     assert np.array_equal(vx, vxo) and np.array_equal(uy, uyo)
+
+
+def test_checkpoint_restart_continues_bit_for_bit(tmp_path):
+    """Stop after 60 iterations, write a checkpoint, restore it into a fresh lattice and continue:
+    identical to the uninterrupted run (the reference has no restart; its state is one array)."""
+    from lbm_b200.lattice import lattice
+    ca, cb = _turek30(), _turek30()
+    la = lattice(ca, make_dirs=False)
+    orc.run_loop(la, ca, n_iters=100)
+    lb = lattice(cb, make_dirs=False)
+    orc.run_loop(lb, cb, n_iters=60)
+    ck = str(tmp_path / "state.npz")
+    lb.save_checkpoint(ck)
+    lc = lattice(cb, make_dirs=False)
+    cb.initialize(lc)                       # same app: allocates, uploads a start state (overwritten)
+    lc.macro(); lc.equilibrium(); lc.collision_stream(); cb.set_bc(lc)   # records obstacles / BC set
+    lc.load_checkpoint(ck)
+    for it in range(60, 100):
+        cb.set_inlets(lc, it)
+        lc.macro(); lc.equilibrium(); lc.collision_stream(); cb.set_bc(lc)
+        cb.observables(lc, it)
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lc, k), getattr(la, k)), k
+    assert np.array_equal(np.array(cb.forces[-40:]), np.array(ca.forces[-40:]))
