@@ -89,3 +89,43 @@ def test_batched_cavity_against_oracle_bitwise():
     orc.run_loop(lo, co)
     for k in ("g_up", "g", "rho", "u"):
         assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
+
+
+def test_full_size_two_update_launch_checksum():
+    """BASELINE config 5 size (32768 x 32768 f64, 154.6 GB): six updates with two-update launches and
+    with single-update launches leave bit-identical populations (compared through on-device
+    checksums; the oracle cannot hold this lattice)."""
+    import torch
+    from lbm_b200.solver import Solver
+    if torch.cuda.get_device_properties(0).total_memory < 170e9:
+        pytest.skip("needs a 180 GB device")
+    n = 32768
+
+    def run(temporal):
+        s = Solver(n, n, tau=0.56)
+        s.set_temporal_blocking(1 if temporal else 0)
+        s.init_equilibrium(1.0)
+        rows = np.zeros((6, s.row_len))
+        for k in range(6):
+            rows[k, 4 * n:5 * n] = 0.1 * (1.0 - np.exp(-(k + 1.0) ** 2 / 8.0))
+        s.set_walls(rows)
+        s.step(1)
+        l0 = s.launches
+        s.step(6, 0, 1)
+        s.sync()
+        cur, _ = s.views()
+        v = cur[:, 2:-2, :]
+        sums = [float(v[q].sum(dtype=torch.float64)) for q in range(9)]
+        bits = [int(v[q].view(torch.int64).sum()) for q in range(9)]      # wrap-around sum of the bit patterns
+        edge = v[:, :, -1].clone().cpu().numpy(), v[:, 0, :].clone().cpu().numpy()
+        launches = s.launches - l0
+        s.close()
+        del cur, v
+        torch.cuda.empty_cache()
+        return sums, bits, edge, launches
+    a = run(True)
+    b = run(False)
+    assert a[3] == 3 and b[3] == 6
+    assert a[0] == b[0] and a[1] == b[1]
+    assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
+    assert abs(sum(a[0]) / n / n - 1.0) < 1e-6            # mean density stays ~1 over six updates
