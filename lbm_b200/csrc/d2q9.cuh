@@ -88,34 +88,51 @@ template <> struct Ar<float, false> {
     }
 };
 
+// Storage of a population.  f64: the population itself (the reference's arrays).  f32: its
+// DEVIATION from the rest-state weight, h_q = f_q - w_q: a float keeps ~7 digits, and f_q ~ 0.03..0.44
+// while the physics lives in deviations of 1e-2 and below, so storing f_q would waste two digits and
+// let rounding drift into u (measured: 1.1e-5 of max|u| after 120 iterations).  Every operation of
+// the update is affine in the populations with weights that sum to one (TRT, IBB, Zou-He, see the
+// notes at each function), so the update is restated exactly on h; host arrays stay populations.
+template <typename T> struct Stored { static constexpr bool dev = false; };
+template <> struct Stored<float> { static constexpr bool dev = true; };
+__host__ __device__ constexpr double weight_of(int q) { return q == 0 ? 4.0 / 9.0 : (q < 5 ? 1.0 / 9.0 : 1.0 / 36.0); }
+
 template <typename T> struct Coef {
     T one_m_omp, om_p;        // q = 0:      (1-om_p) g0 + om_p geq0                 nb.py:26
     T a_self, a_opp, a_eq;    // q >= 1:     1-(om_p+om_m)/2, (om_p-om_m)/2, (om_p+om_m)/2   nb.py:31-35
 };
 
 // rho = sum_q g_q in index order; u = (c . g) / rho     (lattice.py:181-189, oracle orc_macro)
+// Deviation storage: dr = sum_q h_q = rho - 1 (sum_q w_q = 1), momentum unchanged (sum_q c_q w_q = 0).
 template <typename A, typename T>
-__device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy)
+__device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr)
 {
     r = A::add(G[0], G[1]);
 #pragma unroll
     for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
+    dr = r;
+    if (Stored<T>::dev) r = A::add(T(1.0), dr);
     T mx = A::add(A::sub(A::sub(A::add(A::sub(G[1], G[2]), G[5]), G[6]), G[7]), G[8]);
     T my = A::sub(A::add(A::sub(A::add(A::sub(G[3], G[4]), G[5]), G[6]), G[7]), G[8]);
     A::div2(mx, my, r, ux, uy);
 }
 
 // g_eq (nb.py:10-17) followed by the TRT collision (nb.py:25-35); G -> F in place.
+// Deviation storage: g_eq_q - w_q = w_q (dr + rho (t + t^2/2 - v)); the TRT combination has
+// coefficients a_self - a_opp + a_eq + a_opp = 1 and w_q = w_qbar, so it maps h to h unchanged.
 template <typename A, typename T>
-__device__ __forceinline__ void collide(T (&G)[9], T r, T ux, T uy, const Coef<T> &c)
+__device__ __forceinline__ void collide(T (&G)[9], T r, T dr, T ux, T uy, const Coef<T> &c)
 {
+    constexpr bool dev = Stored<T>::dev;
     const T w0 = T(4.0 / 9.0), w1 = T(1.0 / 9.0), w5 = T(1.0 / 36.0);
     const T v = A::mul(T(1.5), A::add(A::mul(ux, ux), A::mul(uy, uy)));
     const T rw0 = A::mul(r, w0), rw1 = A::mul(r, w1), rw5 = A::mul(r, w5);
     // q = 0: t = 0
     {
-        T e = A::sub(A::add(A::add(T(1.0), T(0.0)), T(0.0)), v);
-        T geq = A::mul(e, rw0);
+        T geq;
+        if (dev) geq = A::mul(w0, A::sub(dr, A::mul(r, v)));
+        else     geq = A::mul(A::sub(A::add(A::add(T(1.0), T(0.0)), T(0.0)), v), rw0);
         G[0] = A::add(A::mul(c.one_m_omp, G[0]), A::mul(c.om_p, geq));
     }
     // opposite pairs (q, q+1): t_q = 3 c_q.u, t_qbar = -t_q
@@ -126,8 +143,16 @@ __device__ __forceinline__ void collide(T (&G)[9], T r, T ux, T uy, const Coef<T
         const T rw = k < 2 ? rw1 : rw5;
         const T t = A::mul(T(3.0), s[k]);
         const T h = A::mul(T(0.5), A::mul(t, t));
-        const T eq = A::mul(A::sub(A::add(A::add(T(1.0), t), h), v), rw);
-        const T eb = A::mul(A::sub(A::add(A::sub(T(1.0), t), h), v), rw);
+        T eq, eb;
+        if (dev) {
+            const T w = k < 2 ? w1 : w5;
+            const T hv = A::sub(h, v);
+            eq = A::mul(w, A::add(dr, A::mul(r, A::add(hv, t))));
+            eb = A::mul(w, A::add(dr, A::mul(r, A::sub(hv, t))));
+        } else {
+            eq = A::mul(A::sub(A::add(A::add(T(1.0), t), h), v), rw);
+            eb = A::mul(A::sub(A::add(A::sub(T(1.0), t), h), v), rw);
+        }
         const T gq = G[q], gb = G[qb];
         G[q]  = A::add(A::add(A::sub(A::mul(c.a_self, gq), A::mul(c.a_opp, gb)), A::mul(c.a_eq, eq)),
                        A::mul(c.a_opp, eb));
@@ -161,11 +186,15 @@ template <typename A, typename T> struct ZouHe {
                       A::mul(T(2.0), f));
     }
     static constexpr double c1 = 2.0 / 3.0, c2 = 1.0 / 6.0, c3 = 0.5;
+    // Deviation storage: in each wall's density sum the weights add up to exactly one
+    // (w0 + 2 w_card + 2 (w_card + 2 w_diag) = 1), so  sum(f) = 1 + sum(h);  the three unknown
+    // populations are differences of populations with equal weights plus terms in rho u, unchanged.
+    static __device__ __forceinline__ T full(T s) { return Stored<T>::dev ? A::add(T(1.0), s) : s; }
 
     // nb.py:121-143
     static __device__ __forceinline__ void left(T (&G)[9], T ux, T uy, T &r)
     {
-        r = A::div(sum6(G[0], G[3], G[4], G[2], G[6], G[7]), A::sub(T(1.0), ux));
+        r = A::div(full(sum6(G[0], G[3], G[4], G[2], G[6], G[7])), A::sub(T(1.0), ux));
         const T d = A::sub(G[3], G[4]);
         const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
         G[1] = A::add(G[2], A::mul(k1, ux));
@@ -175,7 +204,7 @@ template <typename A, typename T> struct ZouHe {
     // nb.py:147-169 (velocity) and nb.py:173-195 (pressure: rho given, ux solved)
     static __device__ __forceinline__ void right(T (&G)[9], T &ux, T uy, T &r, bool pressure)
     {
-        const T s = sum6(G[0], G[3], G[4], G[1], G[5], G[8]);
+        const T s = full(sum6(G[0], G[3], G[4], G[1], G[5], G[8]));
         if (pressure) ux = A::sub(A::div(s, r), T(1.0));
         else          r = A::div(s, A::add(T(1.0), ux));
         const T d = A::sub(G[3], G[4]);
@@ -185,13 +214,18 @@ template <typename A, typename T> struct ZouHe {
         G[7] = A::add(A::sub(A::sub(G[8], A::mul(T(c3), d)), A::mul(k2, ux)), A::mul(k3, uy));
     }
     // nb.py:199-221
-    static __device__ __forceinline__ T top_rho(T g0, T g1, T g2, T g3, T g5, T g7, T uy)
+    // dr = rho - 1 without cancellation (deviation storage; used by the corner cells)
+    static __device__ __forceinline__ T top_rho(T g0, T g1, T g2, T g3, T g5, T g7, T uy, T &dr)
     {
-        return A::div(sum6(g0, g1, g2, g3, g5, g7), A::add(T(1.0), uy));
+        const T s = sum6(g0, g1, g2, g3, g5, g7);
+        if (Stored<T>::dev) dr = A::div(A::sub(s, uy), A::add(T(1.0), uy));
+        else dr = T(0.0);
+        return A::div(full(s), A::add(T(1.0), uy));
     }
     static __device__ __forceinline__ void top(T (&G)[9], T ux, T uy, T &r)
     {
-        r = top_rho(G[0], G[1], G[2], G[3], G[5], G[7], uy);
+        T dr;
+        r = top_rho(G[0], G[1], G[2], G[3], G[5], G[7], uy, dr);
         const T d = A::sub(G[1], G[2]);
         const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
         G[4] = A::sub(G[3], A::mul(k1, uy));
@@ -199,22 +233,29 @@ template <typename A, typename T> struct ZouHe {
         G[6] = A::sub(A::sub(A::add(G[5], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
     }
     // nb.py:225-247
-    static __device__ __forceinline__ T bottom_rho(T g0, T g1, T g2, T g4, T g6, T g8, T uy)
+    static __device__ __forceinline__ T bottom_rho(T g0, T g1, T g2, T g4, T g6, T g8, T uy, T &dr)
     {
-        return A::div(sum6(g0, g1, g2, g4, g6, g8), A::sub(T(1.0), uy));
+        const T s = sum6(g0, g1, g2, g4, g6, g8);
+        if (Stored<T>::dev) dr = A::div(A::add(s, uy), A::sub(T(1.0), uy));
+        else dr = T(0.0);
+        return A::div(full(s), A::sub(T(1.0), uy));
     }
     static __device__ __forceinline__ void bottom(T (&G)[9], T ux, T uy, T &r)
     {
-        r = bottom_rho(G[0], G[1], G[2], G[4], G[6], G[8], uy);
+        T dr;
+        r = bottom_rho(G[0], G[1], G[2], G[4], G[6], G[8], uy, dr);
         const T d = A::sub(G[1], G[2]);
         const T k1 = A::mul(T(c1), r), k2 = A::mul(T(c2), r), k3 = A::mul(T(c3), r);
         G[3] = A::add(G[4], A::mul(k1, uy));
         G[5] = A::add(A::add(A::sub(G[6], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
         G[7] = A::add(A::sub(A::add(G[8], A::mul(T(c3), d)), A::mul(k3, ux)), A::mul(k2, uy));
     }
-    // corners nb.py:251-344; (r, ux, uy) copied from the x-neighbour on the horizontal wall
-    static __device__ __forceinline__ void corner(T (&G)[9], bool is_left, bool is_bottom, T r, T ux, T uy)
+    // corners nb.py:251-344; (r, ux, uy) copied from the x-neighbour on the horizontal wall.
+    // Deviation storage: a population set to 0.0 is h = -w; g0 = rho - sum(others) becomes
+    // h0 = (rho - 1) - sum(h others).
+    static __device__ __forceinline__ void corner(T (&G)[9], bool is_left, bool is_bottom, T r, T dr, T ux, T uy)
     {
+        const T zero = Stored<T>::dev ? T(-1.0 / 36.0) : T(0.0);
         const T k23 = A::mul(T(2.0 / 3.0), r), k16 = A::mul(T(1.0 / 6.0), r);
         if (is_left) G[1] = A::add(G[2], A::mul(k23, ux));
         else         G[2] = A::sub(G[1], A::mul(k23, ux));
@@ -222,18 +263,18 @@ template <typename A, typename T> struct ZouHe {
         else           G[4] = A::sub(G[3], A::mul(k23, uy));
         if (is_left && is_bottom) {
             G[5] = A::add(A::add(G[6], A::mul(k16, ux)), A::mul(k16, uy));
-            G[7] = T(0.0); G[8] = T(0.0);
+            G[7] = zero; G[8] = zero;
         } else if (is_left) {
             G[8] = A::sub(A::add(G[7], A::mul(k16, ux)), A::mul(k16, uy));
-            G[5] = T(0.0); G[6] = T(0.0);
+            G[5] = zero; G[6] = zero;
         } else if (!is_bottom) {
             G[6] = A::sub(A::sub(G[5], A::mul(k16, ux)), A::mul(k16, uy));
-            G[7] = T(0.0); G[8] = T(0.0);
+            G[7] = zero; G[8] = zero;
         } else {
             G[7] = A::add(A::sub(G[8], A::mul(k16, ux)), A::mul(k16, uy));
-            G[5] = T(0.0); G[6] = T(0.0);
+            G[5] = zero; G[6] = zero;
         }
-        T g0 = A::sub(r, G[1]);
+        T g0 = A::sub(Stored<T>::dev ? dr : r, G[1]);
 #pragma unroll
         for (int q = 2; q < 9; q++) g0 = A::sub(g0, G[q]);
         G[0] = g0;

@@ -102,11 +102,11 @@ __device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *wal
         const T *uw = B ? ub : ut;
         ux = uw[gxn];
         uy = uw[p.gnx + gxn];
-        T N[9];
+        T N[9], dr;
         src(xn, B ? 0 : p.ny - 1, N);
-        r = B ? ZouHe<A, T>::bottom_rho(N[0], N[1], N[2], N[4], N[6], N[8], uy)
-              : ZouHe<A, T>::top_rho(N[0], N[1], N[2], N[3], N[5], N[7], uy);
-        ZouHe<A, T>::corner(G, L, B, r, ux, uy);
+        r = B ? ZouHe<A, T>::bottom_rho(N[0], N[1], N[2], N[4], N[6], N[8], uy, dr)
+              : ZouHe<A, T>::top_rho(N[0], N[1], N[2], N[3], N[5], N[7], uy, dr);
+        ZouHe<A, T>::corner(G, L, B, r, dr, ux, uy);
     } else if (B) {
         ux = ub[gx]; uy = ub[p.gnx + gx];
         ZouHe<A, T>::bottom(G, ux, uy, r);
@@ -142,14 +142,14 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
         }
     }
     if (MODE != kStreamOnly) {
-        T r, ux, uy;
-        macro<A, T>(G, r, ux, uy);
+        T r, ux, uy, dr;
+        macro<A, T>(G, r, ux, uy, dr);
         if (p.write_macro) {
             p.rho_out[idx] = r;
             p.u_out[idx] = ux;
             p.uy_out[idx] = uy;
         }
-        collide<A, T>(G, r, ux, uy, p.coef);
+        collide<A, T>(G, r, dr, ux, uy, p.coef);
     }
 #pragma unroll
     for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
@@ -187,7 +187,8 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
                 for (int k = 1; k < 9; k++)
                     if (k == qb) G[k] = val;
             }
-            // nb.py:64-67: (g_up_q + g_qbar) c_q
+            // nb.py:64-67: (g_up_q + g_qbar) c_q   (deviation storage: both carry -w_q; the constant
+            // sum_links 2 w_q c_q is added once, in double, on the host)
             const T g0 = A::add(a, val);
             const int s = lp.link_slot[l];
             lp.link_f[2 * s] = (double)A::mul(g0, T(kCx[q]));
@@ -306,9 +307,9 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            T r, ux, uy;
-            macro<A, T>(G[k], r, ux, uy);
-            collide<A, T>(G[k], r, ux, uy, p.coef);
+            T r, ux, uy, dr;
+            macro<A, T>(G[k], r, ux, uy, dr);
+            collide<A, T>(G[k], r, dr, ux, uy, p.coef);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -366,9 +367,9 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            T r, ux, uy;
-            macro<A, T>(G[k], r, ux, uy);
-            collide<A, T>(G[k], r, ux, uy, p.coef);
+            T r, ux, uy, dr;
+            macro<A, T>(G[k], r, ux, uy, dr);
+            collide<A, T>(G[k], r, dr, ux, uy, p.coef);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -403,7 +404,8 @@ probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n
     const GlobalSource<T> gsrc{p};
     gsrc(x, y, G);
     apply_walls<A, T>(p, p.walls, gsrc, x, y, G, r, ux, uy);
-    macro<A, T>(G, r, ux, uy);
+    T dr;
+    macro<A, T>(G, r, ux, uy, dr);
     out[k] = r;
     out[n + k] = ux;
     out[2 * n + k] = uy;
@@ -420,7 +422,8 @@ init_kernel(T *dst, long long plane, int pitch, int nxl, int ny, T r, T ux, T uy
     T E[9];
     equilibrium<Ar<T, STRICT>, T>(E, r, ux, uy);
 #pragma unroll
-    for (int q = 0; q < 9; q++) dst[q * plane + (long long)x * pitch + y] = E[q];
+    for (int q = 0; q < 9; q++)   // device state: deviation from the weight in f32 (d2q9.cuh: Stored)
+        dst[q * plane + (long long)x * pitch + y] = Stored<T>::dev ? E[q] - T(weight_of(q)) : E[q];
 }
 
 // nb_equilibrium on pitched device fields

@@ -77,6 +77,7 @@ struct lbm_handle {
     // forces
     double *d_forces = nullptr;
     int64_t force_cap = 0, force_n = 0;
+    std::vector<double> force_const;   // f32 deviation storage: sum over an obstacle's owned links of 2 w_q c_q
     void *d_probe = nullptr;
     int64_t probe_cap = 0;
     // accounting
@@ -439,6 +440,15 @@ static int upload_populations(lbm_t *h, const void *host, StateKind kind)
     if (!host) return fail(LBM_E_INVALID, "host array is NULL");
     int rc = ensure_state(h);
     if (rc) return rc;
+    std::vector<float> shifted;
+    if (h->cfg.dtype == LBM_F32) {               // f32 state is stored as deviation from the weights
+        const size_t n = (size_t)h->cfg.nxl * h->cfg.ny;
+        const float *g = static_cast<const float *>(host);
+        shifted.resize(9 * n);
+        for (int q = 0; q < 9; q++)
+            for (size_t k = 0; k < n; k++) shifted[q * n + k] = (float)((double)g[q * n + k] - weight_of(q));
+        host = shifted.data();
+    }
     rc = copy_field_h2d(h, elem_ptr(h, h->cur, 0), h->lay.plane, host, 9);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));  // the caller may free the host array on return
@@ -520,6 +530,7 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     free_links(h);
+    h->force_const.clear();
     if (h->d_forces) { cudaFree(h->d_forces); h->d_forces = nullptr; h->force_cap = 0; }
     if (n_obstacles <= 0) return LBM_OK;
     if (!offsets || !ijq) return fail(LBM_E_INVALID, "NULL link arrays");
@@ -563,6 +574,13 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
             }
         }
         if (i < x0 || i >= x0 + nxl) continue;  // owned by another slab
+        if (h->cfg.dtype == LBM_F32) {
+            int o = 0;
+            while (o + 1 < n_obstacles && offsets[o + 1] <= k) o++;
+            if ((int)h->force_const.size() < 2 * n_obstacles) h->force_const.assign(2 * n_obstacles, 0.0);
+            h->force_const[2 * o] += 2.0 * weight_of((int)q) * cx_of((int)q);
+            h->force_const[2 * o + 1] += 2.0 * weight_of((int)q) * cy_of((int)q);
+        }
         l.x = (int)(i - x0);
         l.y = (int)j;
         links.push_back(l);
@@ -770,6 +788,9 @@ int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
     if (n == 0) return LBM_OK;
     CUDA_TRY(cudaMemcpyAsync(out, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->force_const.empty())
+        for (int64_t s = 0; s < n; s++)
+            for (int k = 0; k < 2 * nobs; k++) out[s * 2 * nobs + k] += h->force_const[k];
     return LBM_OK;
 }
 
@@ -805,6 +826,8 @@ int lbm_forces_now(lbm_t *h, double *out)
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "lbm_forces_now: %s", cudaGetErrorString(e));
+        if (!rc && !h->force_const.empty())
+            for (int k = 0; k < 2 * nobs; k++) out[k] += h->force_const[k];
     }
     cudaFree(d_out);
     return rc;
@@ -823,7 +846,14 @@ int lbm_get_populations(lbm_t *h, int32_t which, void *host)
         else if (h->kind == kHaveF && h->other_has_g) src = h->cur ^ 1;
         else return fail(LBM_E_STATE, "streamed populations not materialised: call lbm_apply_bc first");
     } else return fail(LBM_E_INVALID, "bad `which`");
-    return copy_field_d2h(h, elem_ptr(h, src, 0), h->lay.plane, host, 9);
+    int rc = copy_field_d2h(h, elem_ptr(h, src, 0), h->lay.plane, host, 9);
+    if (!rc && h->cfg.dtype == LBM_F32) {        // deviation storage -> populations
+        const size_t n = (size_t)h->cfg.nxl * h->cfg.ny;
+        float *g = static_cast<float *>(host);
+        for (int q = 0; q < 9; q++)
+            for (size_t k = 0; k < n; k++) g[q * n + k] = (float)((double)g[q * n + k] + weight_of(q));
+    }
+    return rc;
 }
 
 int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host)

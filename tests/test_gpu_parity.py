@@ -91,12 +91,18 @@ def test_baseline_configs_bounded_horizon(name, n):
         assert np.max(np.abs(f - fo)) < 1e-6
 
 
-@pytest.mark.parametrize("name,n", [("cavity32", 150), ("turek30", 60)])
+@pytest.mark.parametrize("name,n", [("cavity32", 150), ("turek30", 120), ("poiseuille20", 100), ("cavity200", 1500)])
 def test_f32_variant(name, n):
+    """f32 populations are stored as deviations from the weights (d2q9.cuh: Stored); measured on B200:
+    1e-7 on populations/density, 2e-7..2e-6 on u (1.1e-5 with plain f32 storage).  Bound: 1e-5
+    (north_star), asserted with a factor 2 in hand."""
     lat_g, c_gpu, lat_o, c_cpu = run_both(name, n, dtype="f32")
     assert lat_g.g_up.dtype == np.float32
     for k in ("g", "g_up", "rho", "u"):
-        assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 1e-5, k
+        assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 5e-6, k
+    if c_gpu.forces:
+        f, fo = np.array(c_gpu.forces), np.array(c_cpu.forces)
+        assert np.max(np.abs(f - fo)) < 1e-4 * np.max(np.abs(fo))
 
 
 def test_equilibrium_entry_point_matches_golden():
