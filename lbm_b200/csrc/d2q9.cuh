@@ -22,6 +22,7 @@ __host__ __device__ constexpr int cy_of(int q) { return q == 3 || q == 5 || q ==
 template <typename T, bool STRICT> struct Ar;
 __device__ __forceinline__ double rcp_fast(double b);
 template <> struct Ar<double, true> {
+    static constexpr bool strict = true;
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
@@ -33,6 +34,7 @@ template <> struct Ar<double, true> {
     }
 };
 template <> struct Ar<float, true> {
+    static constexpr bool strict = true;
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -46,14 +48,17 @@ template <> struct Ar<float, true> {
 // FUSED division: the IEEE double division of nvcc is a ~60-instruction subroutine call, and the
 // update kernels are instruction-issue bound once the HBM traffic is halved (profiles/README.md).
 // The divisor is always a density or 1 +- u (normal range, far from 0/inf), so a reciprocal seed
-// (MUFU.RCP64H) refined by two Newton steps and one residual correction of the quotient is used:
+// (MUFU.RCP64H) refined by three Newton steps is used (single quotients add a residual correction):
 // no special-case handling, result within 1 ulp of the correctly rounded quotient.  (The
 // reference's Numba kernels run with fastmath, which licenses the same reciprocal rewrite.)
 __device__ __forceinline__ double rcp_fast(double b)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    // the seed (MUFU.RCP64H) is good to ~8 bits: three quadratic steps -> 2^-64
     double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
     y = fma(y, e, y);
     e = fma(-b, y, 1.0);
     return fma(y, e, y);
@@ -64,18 +69,20 @@ __device__ __forceinline__ double mul_rcp(double a, double b, double y /* ~1/b *
     return fma(fma(-b, q, a), y, q);
 }
 template <> struct Ar<double, false> {
+    static constexpr bool strict = false;
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
     static __device__ __forceinline__ double div(double a, double b) { return mul_rcp(a, b, rcp_fast(b)); }
     static __device__ __forceinline__ void div2(double a0, double a1, double b, double &q0, double &q1)
     {
-        const double y = rcp_fast(b);
-        q0 = mul_rcp(a0, b, y);
-        q1 = mul_rcp(a1, b, y);
+        const double y = rcp_fast(b);   // |y b - 1| <= ~1 ulp: the two quotients are good to 1.5 ulp
+        q0 = a0 * y;
+        q1 = a1 * y;
     }
 };
 template <> struct Ar<float, false> {
+    static constexpr bool strict = false;
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
@@ -101,6 +108,8 @@ __host__ __device__ constexpr double weight_of(int q) { return q == 0 ? 4.0 / 9.
 template <typename T> struct Coef {
     T one_m_omp, om_p;        // q = 0:      (1-om_p) g0 + om_p geq0                 nb.py:26
     T a_self, a_opp, a_eq;    // q >= 1:     1-(om_p+om_m)/2, (om_p-om_m)/2, (om_p+om_m)/2   nb.py:31-35
+    // FUSED arithmetic (collide_fused): w_q om_p for the three weight classes, 4.5 w_q om_p, 3 w_q om_m
+    T wp0, wp1, wp5, wq1, wq5, wm1, wm5;
 };
 
 // rho = sum_q g_q in index order; u = (c . g) / rho     (lattice.py:181-189, oracle orc_macro)
@@ -113,17 +122,60 @@ __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr
     for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
     dr = r;
     if (Stored<T>::dev) r = A::add(T(1.0), dr);
-    T mx = A::add(A::sub(A::sub(A::add(A::sub(G[1], G[2]), G[5]), G[6]), G[7]), G[8]);
-    T my = A::sub(A::add(A::sub(A::add(A::sub(G[3], G[4]), G[5]), G[6]), G[7]), G[8]);
+    T mx, my;
+    if (A::strict) {
+        mx = A::add(A::sub(A::sub(A::add(A::sub(G[1], G[2]), G[5]), G[6]), G[7]), G[8]);
+        my = A::sub(A::add(A::sub(A::add(A::sub(G[3], G[4]), G[5]), G[6]), G[7]), G[8]);
+    } else {   // same sums with the two diagonal differences shared
+        const T d56 = G[5] - G[6], d78 = G[7] - G[8];
+        mx = ((G[1] - G[2]) + d56) - d78;
+        my = ((G[3] - G[4]) + d56) + d78;
+    }
     A::div2(mx, my, r, ux, uy);
 }
 
 // g_eq (nb.py:10-17) followed by the TRT collision (nb.py:25-35); G -> F in place.
 // Deviation storage: g_eq_q - w_q = w_q (dr + rho (t + t^2/2 - v)); the TRT combination has
 // coefficients a_self - a_opp + a_eq + a_opp = 1 and w_q = w_qbar, so it maps h to h unchanged.
+// FUSED arithmetic: the same collision written in the symmetric / antisymmetric parts of the
+// equilibrium.  With  eq_s = (geq_q + geq_qbar)/2 = w r (1 + 4.5 s^2 - v),  eq_a = (geq_q - geq_qbar)/2
+// = 3 w r s  (s = c_q.u)  and  a_eq + a_opp = om_p,  a_eq - a_opp = om_m  the TRT update of a pair is
+//     F_q    = a_self g_q    - a_opp g_qbar + om_p eq_s + om_m eq_a
+//     F_qbar = a_self g_qbar - a_opp g_q    + om_p eq_s - om_m eq_a
+// 9 FP64 instructions per pair instead of 19 (the update kernels are FP64-issue and power bound once
+// the HBM traffic is halved).  Algebraically identical to nb.py:10-17 + 25-35; rounding differs at the
+// 1e-16 level like any FMA contraction does.  Deviation storage (f32): eq_s - w = w (dr + r (4.5 s^2 - v)).
+template <typename T>
+__device__ __forceinline__ void collide_fused(T (&G)[9], T r, T dr, T ux, T uy, const Coef<T> &c)
+{
+    constexpr bool dev = Stored<T>::dev;
+    const T v = T(1.5) * (ux * ux + uy * uy);
+    const T rp0 = r * c.wp0, rp1 = r * c.wp1, rp5 = r * c.wp5;     // om_p w r
+    const T rq1 = r * c.wq1, rq5 = r * c.wq5;                      // 4.5 om_p w r
+    const T rm1 = r * c.wm1, rm5 = r * c.wm5;                      // 3 om_m w r
+    const T b0 = dev ? c.wp0 * dr - rp0 * v : rp0 - rp0 * v;       // om_p eq_s at s = 0
+    const T b1 = dev ? c.wp1 * dr - rp1 * v : rp1 - rp1 * v;
+    const T b5 = dev ? c.wp5 * dr - rp5 * v : rp5 - rp5 * v;
+    G[0] = c.one_m_omp * G[0] + b0;
+    const T s[4] = {ux, uy, ux + uy, uy - ux};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int q = 2 * k + 1, qb = q + 1;
+        const T P = (k < 2 ? rq1 : rq5) * (s[k] * s[k]) + (k < 2 ? b1 : b5);
+        const T M = (k < 2 ? rm1 : rm5) * s[k];
+        const T gq = G[q], gb = G[qb];
+        G[q]  = c.a_self * gq + ((P + M) - c.a_opp * gb);
+        G[qb] = c.a_self * gb + ((P - M) - c.a_opp * gq);
+    }
+}
+
 template <typename A, typename T>
 __device__ __forceinline__ void collide(T (&G)[9], T r, T dr, T ux, T uy, const Coef<T> &c)
 {
+    if (!A::strict) {
+        collide_fused<T>(G, r, dr, ux, uy, c);
+        return;
+    }
     constexpr bool dev = Stored<T>::dev;
     const T w0 = T(4.0 / 9.0), w1 = T(1.0 / 9.0), w5 = T(1.0 / 36.0);
     const T v = A::mul(T(1.5), A::add(A::mul(ux, ux), A::mul(uy, uy)));

@@ -328,18 +328,14 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
     if (p.pf_ahead > 0) {
         const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.pf_ahead;
         const int by = (int)(lin / gridDim.x), bx = (int)(lin - (long long)by * gridDim.x);
-        if (by < (int)gridDim.y) {
-            const int px0 = p.xa + by * TX - 2, py0 = bx * TY - 2;
-            constexpr int LPR = ((TY + 4) * (int)sizeof(T) + 127) / 128 + 1;   // 128 B lines per source row
-            constexpr int NPF = 9 * (TX + 4) * LPR;
-            for (int k = threadIdx.x; k < NPF; k += NT) {
-                const int q = k / ((TX + 4) * LPR), r = k - q * ((TX + 4) * LPR);
-                const int xr = r / LPR, l = r - xr * LPR;
-                const int x = px0 + xr;
-                if (x >= p.x_lo - 1 && x < p.x_hi + 1) {
-                    const T *a = p.ctr[q] + (long long)x * p.pitch + max(py0, 0) + l * (128 / (int)sizeof(T));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-                }
+        constexpr int PADE = 16 / (int)sizeof(T);                       // keeps the row start 16 B aligned
+        constexpr unsigned ROWB = (TY + 2 * PADE) * (unsigned)sizeof(T); // bytes of one source row
+        if (by < (int)gridDim.y && threadIdx.x < 9 * (TX + 4)) {        // one bulk prefetch per plane and row
+            const int q = threadIdx.x / (TX + 4), xr = threadIdx.x - q * (TX + 4);
+            const int x = p.xa + by * TX - 2 + xr, y0 = bx * TY - PADE;
+            if (x >= p.x_lo - 1 && x < p.x_hi + 1 && y0 >= 0 && y0 + TY + 2 * PADE <= p.pitch) {
+                const T *a = p.ctr[q] + (long long)x * p.pitch + y0;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(ROWB) : "memory");
             }
         }
     }

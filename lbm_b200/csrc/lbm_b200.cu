@@ -186,6 +186,9 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.coef.a_self = T(1.0 - 0.5 * (op + om));
     p.coef.a_opp = T(0.5 * (op - om));
     p.coef.a_eq = T(0.5 * (op + om));
+    p.coef.wp0 = T(op * 4.0 / 9.0); p.coef.wp1 = T(op / 9.0); p.coef.wp5 = T(op / 36.0);
+    p.coef.wq1 = T(4.5 * op / 9.0); p.coef.wq5 = T(4.5 * op / 36.0);
+    p.coef.wm1 = T(3.0 * om / 9.0); p.coef.wm5 = T(3.0 * om / 36.0);
     p.walls = h->walls ? static_cast<const T *>(h->walls) + row * h->row_len : nullptr;
     p.walls2 = nullptr;
     p.rho_out = static_cast<T *>(h->rho);

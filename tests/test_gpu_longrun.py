@@ -88,6 +88,10 @@ def test_array_config4_many_obstacles():
     lat, n = _gpu_run(cg, batch=1024)
     lo = orc.OracleLattice(co)
     assert orc.run_loop(lo, co) == n == 2500
+    # the default ramp (sigma = 10 nx = 9000) leaves max|u| ~ 1e-3 after 2500 iterations, while the
+    # pressure outlet computes u_x = sum/rho - 1 with an absolute rounding floor of ~1e-14: measure u
+    # against the lattice velocity scale u_lbm, not against the still tiny max|u|
     for k in ("rho", "u", "g_up", "g"):
         a, b = getattr(lat, k), getattr(lo, k)
-        assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 1e-10, k
+        scale = max(np.max(np.abs(b)), cg.u_lbm) if k == "u" else np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) / scale < 1e-10, k
