@@ -93,7 +93,7 @@ typedef struct lbm_layout {
     int64_t plane;  /* elements between consecutive q */
     int64_t pitch;  /* elements between consecutive x */
     int64_t elem_size;
-    int64_t halo;   /* halo columns on each side (2) */
+    int64_t halo;   /* halo columns on each side (4) */
 } lbm_layout;
 
 int lbm_abi_version(void);
@@ -158,6 +158,17 @@ int lbm_flip(lbm_t *h);
  * lbm_set_temporal_blocking(h, 0) was called; enable < 0 forces pairing on any size (tests). */
 int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2);
 int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
+/* depth = 2, 3 or 4 consecutive updates (wall rows rows[0..depth-1]) of local columns [xa, xb) in
+ * ONE launch (wavefront temporal blocking: a block sweeps a strip of rows along x, the updates
+ * form a pipeline through shared memory, the source is streamed in by TMA bulk copies), without
+ * flipping; reads columns xa-depth .. xb+depth-1.  Not available with obstacle links.
+ * lbm_set_temporal_depth bounds the updates per launch that lbm_step chooses by itself
+ * (1 = never more than one, 2 = step2_kernel pairs, 3/4 = wavefront launches; default 4). */
+int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int64_t *rows);
+int lbm_set_temporal_depth(lbm_t *h, int32_t depth);
+/* Launch-shape knobs (measurement, tests): "wave_chunk" = columns swept by one block of a
+ * wavefront launch (default 512), "pf_ahead" = L2 prefetch distance of step2_kernel in blocks. */
+int lbm_set_tuning(lbm_t *h, const char *key, int64_t value);
 
 /* Stream + (I)BB + Zou-He of the current F with wall row `row`, no collision: materialises the
  * reference's g (nb_col_str stream part + set_bc) in the other buffer, overwrites rho,u on the

@@ -20,7 +20,7 @@ namespace lbm {
 
 enum Mode { kFused = 0, kCollideOnly = 1, kStreamOnly = 2 };
 constexpr int kBlock = 256;
-constexpr int kHalo = 2;       // halo columns on each side of a slab (2: temporal blocking)
+constexpr int kHalo = 4;       // halo columns on each side of a slab (= deepest temporal blocking)
 
 template <typename T> struct StepParams {
     const T *pull[9];       // pull[q][x*pitch + y] == F_q(x - cx_q, y - cy_q)   (local x, may be -1 .. nxl)
@@ -40,6 +40,8 @@ template <typename T> struct StepParams {
     int right_pressure;
     int write_macro;
     int pf_ahead;           // step2_kernel: L2 prefetch distance in blocks (0 = off)
+    const T *wrow[4];       // stepw_kernel: wall rows of the (up to four) updates of one launch
+    int chunk;              // stepw_kernel: columns swept by one block
 };
 
 struct LinkParams {
@@ -375,6 +377,190 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
                 for (int q = 0; q < 9; q++) p.dst[q][idx] = G[k][q];
             }
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// D updates per launch: wavefront temporal blocking (stepw_kernel).
+//
+// A block owns a strip of TYB rows (y, the contiguous axis) and sweeps it along x over a chunk of
+// columns.  The D updates form a software pipeline of D stages, one group of TYB threads each:
+// at sweep step s stage k computes update k+1 of column  xs0 + s - 2k  from the three columns
+// x-1, x, x+1 of the previous level and writes the result into its own ring of 4 columns in shared
+// memory (the last stage stores to global memory).  Level 0 -- the source populations -- is
+// streamed into an 8-column shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier) issued
+// by a dedicated producer warp five columns ahead of their use, so the compute threads never touch
+// global memory on the load side and never compute a global load address.
+//
+//   * HBM traffic: one read + one write of the populations per D updates (144/D bytes per lattice
+//     update in f64), plus the re-read of the 2*M0 margin rows of each strip.
+//   * Redundant work: only along y.  A strip loses one row per side and update, so TYB rows yield
+//     TYB - 2*PAD output rows (PAD >= D-1, rounded to the 16-byte granularity of the bulk copies):
+//     128 -> 120 rows for D = 4 in f64, 6.7 % (the 8 x 64 tiles of step2_kernel recompute 14.5 %
+//     for D = 2).  Along x a chunk recomputes 2(D-1) columns per 512.
+//   * One __syncthreads per sweep step orders the ring traffic: stage k reads columns x-1..x+1 of
+//     level k-1 while stage k-1 writes column x+2 = slot (x-2) & 3.
+//   * Same per-cell device functions as step_kernel, hence bit-identical results.
+//
+// Corner cells need the pulled populations of their x-neighbour on the horizontal wall
+// (nb.py:254-257).  For the right wall those are columns x-2..x of the previous level, all still in
+// the rings (the stage before does not run past the wall).  The LEFT corners would need column x+2,
+// which the stage before is writing in the same step, so they are deferred by one step: the two
+// corner threads process cell (x_wl, y) together with column x_wl + 1.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+    while (!mbar_try_wait(b, parity)) {}
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+template <typename T, int TYB> struct Wave {
+    static constexpr int M0 = 16 / (int)sizeof(T);      // bulk copies move multiples of 16 bytes
+    static constexpr int ROWS = TYB + 2 * M0;           // rows of one plane-column in a ring: t = -M0 .. TYB+M0-1
+    static constexpr int COL = 9 * ROWS;                // elements of one ring slot (a column of the strip)
+    static constexpr int R = 4;                         // slots of the rings between stages
+    static constexpr int LAG = 2;                       // columns between consecutive stages
+    static constexpr int HDR = 128;                     // mbarriers
+    __host__ __device__ static constexpr int pad(int D) { return (D - 1 + M0 - 1) / M0 * M0; }
+    __host__ __device__ static constexpr int out_rows(int D) { return TYB - 2 * pad(D); }
+    __host__ __device__ static constexpr size_t smem(int D, int R0) { return HDR + (size_t)(R0 + (D - 1) * R) * COL * sizeof(T); }
+};
+
+template <typename T, int ROWS, int COL> struct RingSource {
+    const T *base;          // (slot 0, q 0, row of t = 0)
+    int mask;               // slots - 1
+    int ys;                 // lattice y of t = 0
+    __device__ __forceinline__ void operator()(int x, int y, T (&G)[9]) const
+    {
+        const int t = y - ys;
+        const T *c0 = base + (x & mask) * COL + t;
+        const T *cm = base + ((x - 1) & mask) * COL + t;    // column x-1 feeds the populations with c_x = +1
+        const T *cp = base + ((x + 1) & mask) * COL + t;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
+            G[q] = c[q * ROWS - cy_of(q)];
+        }
+    }
+};
+
+template <typename T, bool STRICT, int D, int TYB, int R0, int MINB>
+__global__ void __launch_bounds__(D * TYB + 32, MINB)
+stepw_kernel(const __grid_constant__ StepParams<T> p)
+{
+    using A = Ar<T, STRICT>;
+    using W = Wave<T, TYB>;
+    constexpr int M0 = W::M0, ROWS = W::ROWS, COL = W::COL, R = W::R, LAG = W::LAG;
+    constexpr int PAD = W::pad(D), TO = W::out_rows(D);
+    constexpr int NC = D * TYB, NT = NC + 32;            // compute threads + one producer warp
+    static_assert(TO > 0 && (R0 & (R0 - 1)) == 0 && R0 >= 8, "bad wavefront geometry");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    T *lvl0 = reinterpret_cast<T *>(smem_raw + W::HDR);      // [R0][9][ROWS]   level 0 (TMA ring)
+    T *lvl = lvl0 + R0 * COL;                                // [D-1][R][9][ROWS] levels 1 .. D-1
+
+    const int stage = threadIdx.x / TYB, t = threadIdx.x - stage * TYB;
+    const int ys = (int)blockIdx.x * TO - PAD, y = ys + t;
+    const int ca = p.xa + (int)blockIdx.y * p.chunk, cb = min(ca + p.chunk, p.xb);   // output columns [ca, cb)
+    const int xs0 = ca - (D - 1);                            // first column of stage 0
+    const int c_first = xs0 - 2, c_last = cb + D - 1;        // level-0 columns that are loaded
+    const int nsteps = (cb - ca) + 2 * (D - 1) + LAG * (D - 1);
+    // stage k computes columns [ca - (D-1-k), cb + (D-1-k)) that exist in the global lattice
+    const int lo = max(ca - (D - 1 - stage), p.x_lo), hi = min(cb + (D - 1 - stage), p.x_hi);
+    const bool row_ok = y >= 0 && y < p.ny;
+    const bool edge_row = y == 0 || y == p.ny - 1;
+    const bool store_row = t >= PAD && t < PAD + TO;
+
+    auto load_column = [&](int c) {                          // one thread: 9 bulk copies, one per plane
+        unsigned long long *b = mbar + (c & (R0 - 1));
+        mbar_expect_tx(b, 9u * ROWS * (unsigned)sizeof(T));
+        const int cc = min(max(c, -kHalo), p.nxl + kHalo - 1);     // stay inside the allocation
+        T *d = lvl0 + (c & (R0 - 1)) * COL;
+        const long long off = (long long)cc * p.pitch + (ys - M0);
+#pragma unroll
+        for (int q = 0; q < 9; q++) bulk_g2s(d + q * ROWS, p.ctr[q] + off, ROWS * (unsigned)sizeof(T), b);
+    };
+
+    if (threadIdx.x == NC) {
+        for (int i = 0; i < R0; i++) mbar_init(mbar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- producer warp: one lane streams the level-0 columns in, five columns ahead of stage 0 ----
+    if (threadIdx.x >= NC) {
+        if (threadIdx.x == NC)
+            for (int c = c_first; c < c_first + R0 && c <= c_last; c++) load_column(c);
+        for (int s = 0; s < nsteps; s++) {
+            // the ring holds columns x-2 .. x+R0-3 of stage 0's column x = xs0 + s; x-3 was last read in step s-1
+            if (threadIdx.x == NC && s >= 1 && xs0 + s + R0 - 3 <= c_last) load_column(xs0 + s + R0 - 3);
+            __syncwarp();
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        }
+        return;
+    }
+
+    const RingSource<T, ROWS, COL> src{(stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0,
+                                       stage == 0 ? R0 - 1 : R - 1, ys};
+    T *const out = lvl + stage * R * COL + M0 + t;           // own ring (stages 0 .. D-2)
+    const T *const walls = p.wrow[stage];
+
+    for (int s = 0; s < nsteps; s++) {
+        const int x = xs0 + s - LAG * stage;
+        if (stage == 0) {
+            if (s == 0)
+                for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
+            const int c = x + 1;
+            if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
+        }
+        if (row_ok && x >= lo && x < hi) {
+            // left corners wait for the next column (see above); then two cells in one step
+            int n = 1, xc = x;
+            if (edge_row && x == p.x_wl) n = 0;
+            if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
+            for (; n > 0; n--, xc--) {
+                T G[9], r, ux, uy, dr;
+                src(xc, y, G);
+                apply_walls<A, T>(p, walls, src, xc, y, G, r, ux, uy);
+                macro<A, T>(G, r, ux, uy, dr);
+                collide<A, T>(G, r, dr, ux, uy, p.coef);
+                if (stage == D - 1) {
+                    if (store_row) {
+                        const int idx = xc * p.pitch + y;
+#pragma unroll
+                        for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+                    }
+                } else {
+                    T *o = out + (xc & (R - 1)) * COL;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
     }
 }
 

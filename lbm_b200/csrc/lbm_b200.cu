@@ -55,7 +55,11 @@ struct lbm_handle {
     int cur = 0;
     StateKind kind = kNone;
     bool other_has_g = false;     // other buffer holds stream+BC of current F (lbm_apply_bc)
-    bool temporal = true;         // pair updates into step2_kernel launches where possible
+    bool temporal = true;         // several updates per launch (step2_kernel / stepw_kernel) where possible
+    int depth = 4;                // most updates per launch (lbm_set_temporal_depth)
+    int wave_chunk = 512;         // columns swept by one block of stepw_kernel
+    int wave_rows = 128;          // rows of a strip of stepw_kernel (128, or 64 with two blocks per SM)
+    bool wave_attr_set[5] = {false, false, false, false, false};
     int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
     bool tb_force = false;        // pair updates even on small lattices (tests)
     bool smem_attr_set = false;
@@ -94,10 +98,11 @@ static void compute_layout(const lbm_cfg &c, lbm_layout &l)
     l.pitch = round_up(c.ny, 128 / l.elem_size);
     l.halo = kHalo;
     l.plane = (c.nxl + 2 * kHalo) * l.pitch;
-    // one guard column before and after everything so that y-1 / y+1 pulls at the first and
-    // last halo column stay inside the allocation
-    l.origin = l.pitch /*guard*/ + kHalo * l.pitch /*halo columns x = -2, -1*/;
-    l.elems = 9 * l.plane + 2 * l.pitch;
+    // a guard before and after everything so that y-1 / y+1 pulls at the first and last halo
+    // column, and the margin rows of the bulk copies of stepw_kernel, stay inside the allocation
+    const int64_t guard = std::max<int64_t>(l.pitch, 256);
+    l.origin = guard + kHalo * l.pitch /*halo columns x = -kHalo .. -1*/;
+    l.elems = 9 * l.plane + 2 * guard;
 }
 
 static int check_cfg(const lbm_cfg *c)
@@ -198,6 +203,8 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.right_pressure = h->cfg.right_wall == LBM_RIGHT_PRESSURE;
     p.write_macro = 0;
     p.pf_ahead = h->pf_ahead;
+    for (int k = 0; k < 4; k++) p.wrow[k] = nullptr;
+    p.chunk = h->wave_chunk;
     lp.n_cells = h->n_cells;
     lp.n_links = h->n_links;
     lp.n_obs = h->n_obs;
@@ -256,6 +263,69 @@ static int launch_step2(lbm_handle *h, int src, int dst, int xa, int xb, int64_t
                       : launch_step2_t<double, false>(h, src, dst, xa, xb, row1, row2);
     return strict ? launch_step2_t<float, true>(h, src, dst, xa, xb, row1, row2)
                   : launch_step2_t<float, false>(h, src, dst, xa, xb, row1, row2);
+}
+
+
+// ---- wavefront temporal blocking: D updates per launch ----------------------------------
+constexpr int kWaveR0 = 8;
+
+template <typename T, bool STRICT, int D, int kWaveRows, int MINB>
+static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const int64_t *rows)
+{
+    using W = Wave<T, kWaveRows>;
+    StepParams<T> p;
+    LinkParams lp;
+    fill_params<T>(h, p, lp, src, dst, xa, xb, rows[0], 0);
+    for (int k = 0; k < D; k++) p.wrow[k] = static_cast<const T *>(h->walls) + rows[k] * h->row_len;
+    // columns that exist in the global lattice; without a wall the slab continues into the halo
+    p.x_lo = h->cfg.x0 == 0 ? 0 : -(1 << 20);
+    p.x_hi = h->cfg.x0 + h->cfg.nxl == h->cfg.nx ? (int)h->cfg.nxl : (int)h->cfg.nxl + (1 << 20);
+    // chunks of columns; a right-wall corner reads its x-neighbour's pulled populations from the
+    // rings, so the chunk that holds the right wall must be at least two columns wide
+    const int n = xb - xa;
+    int chunk = std::max(16, h->wave_chunk);
+    while (n > chunk && n % chunk == 1) chunk++;
+    p.chunk = chunk;
+    constexpr size_t smem = W::smem(D, kWaveR0);
+    auto kern = stepw_kernel<T, STRICT, D, kWaveRows, kWaveR0, MINB>;
+    if (!h->wave_attr_set[D]) {   // per handle: the attribute belongs to the handle's device
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->wave_attr_set[D] = true;
+    }
+    constexpr int TO = W::out_rows(D);
+    dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)((n + chunk - 1) / chunk)), block(D * kWaveRows + 32);
+    if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one wavefront launch");
+    kern<<<grid, block, smem, h->stream>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+template <typename T, bool STRICT, int D>
+static int launch_stepw_t(lbm_handle *h, int src, int dst, int xa, int xb, const int64_t *rows)
+{
+    if (h->wave_rows == 64) return launch_stepw_v<T, STRICT, D, 64, 2>(h, src, dst, xa, xb, rows);
+    return launch_stepw_v<T, STRICT, D, 128, 1>(h, src, dst, xa, xb, rows);
+}
+
+template <typename T, bool STRICT>
+static int launch_stepw_d(lbm_handle *h, int src, int dst, int xa, int xb, int depth, const int64_t *rows)
+{
+    switch (depth) {
+    case 2: return launch_stepw_t<T, STRICT, 2>(h, src, dst, xa, xb, rows);
+    case 3: return launch_stepw_t<T, STRICT, 3>(h, src, dst, xa, xb, rows);
+    default: return launch_stepw_t<T, STRICT, 4>(h, src, dst, xa, xb, rows);
+    }
+}
+
+static int launch_stepw(lbm_handle *h, int src, int dst, int xa, int xb, int depth, const int64_t *rows)
+{
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    if (h->cfg.dtype == LBM_F64)
+        return strict ? launch_stepw_d<double, true>(h, src, dst, xa, xb, depth, rows)
+                      : launch_stepw_d<double, false>(h, src, dst, xa, xb, depth, rows);
+    return strict ? launch_stepw_d<float, true>(h, src, dst, xa, xb, depth, rows)
+                  : launch_stepw_d<float, false>(h, src, dst, xa, xb, depth, rows);
 }
 
 template <typename T, bool STRICT>
@@ -698,17 +768,25 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         const bool last = s == n_updates - 1;
         const bool wm = last && (flags & LBM_STEP_MACRO_LAST);
         const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
-        // two updates in one launch when neither needs obstacle links or macro output
-        const bool wm_next = (s + 1 == n_updates - 1) && (flags & LBM_STEP_MACRO_LAST);
-        // ... and the lattice has enough 8 x 64 tiles for two full waves of 4 blocks per SM
-        // (below that the single-update kernel is faster: small lattices are latency bound)
+        // several updates in one launch when none of them needs obstacle links or macro output
+        // (the update that writes rho,u is the last one of the call and runs alone) ...
+        const int64_t plain = n_updates - s - ((flags & LBM_STEP_MACRO_LAST) ? 1 : 0);
+        // ... and the lattice is large enough to profit: below two full waves of 8 x 64 tiles at 4
+        // blocks per SM the single-update kernel is faster (small lattices are latency bound)
         const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * 148 || h->tb_force;
-        if (h->temporal && big && mode == kFused && h->n_obs == 0 && s + 1 < n_updates && !wm_next && h->cfg.nxl >= 4) {
-            rc = launch_step2(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride,
-                              first_row + (s + 1) * row_stride);
+        if (h->temporal && big && mode == kFused && h->n_obs == 0 && plain >= 2 && h->cfg.nxl >= 4) {
+            const int d = (int)std::min<int64_t>(plain, h->depth);
+            if (d >= 3 || (d == 2 && h->depth > 2)) {
+                int64_t rows[4];
+                for (int k = 0; k < d; k++) rows[k] = first_row + (s + k) * row_stride;
+                rc = launch_stepw(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, d, rows);
+            } else {
+                rc = launch_step2(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride,
+                                  first_row + (s + 1) * row_stride);
+            }
             if (rc) return rc;
             h->cur ^= 1;
-            s++;
+            s += d - 1;
             continue;
         }
         rc = launch_step(h, mode, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row + s * row_stride, s, wm);
@@ -747,6 +825,45 @@ int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t ro
     if (!rc) rc = check_row(h, row2);
     if (rc) return rc;
     return launch_step2(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, row1, row2);
+}
+
+int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int64_t *rows)
+{
+    CHECK_H(h);
+    if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_stepn_columns needs post-collision populations");
+    if (h->n_obs > 0) return fail(LBM_E_UNSUPPORTED, "multi-update launches do not handle obstacle links");
+    if (depth < 2 || depth > 4 || !rows) return fail(LBM_E_INVALID, "depth must be 2, 3 or 4 (with one wall row each)");
+    if (xa < 0 || xb > h->cfg.nxl || xb - xa < 2) return fail(LBM_E_INVALID, "bad column range (need at least 2 columns)");
+    for (int k = 0; k < depth; k++) {
+        int rc = check_row(h, rows[k]);
+        if (rc) return rc;
+    }
+    return launch_stepw(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, depth, rows);
+}
+
+int lbm_set_temporal_depth(lbm_t *h, int32_t depth)
+{
+    if (!h) return fail(LBM_E_INVALID, "handle is NULL");
+    if (depth < 1 || depth > 4) return fail(LBM_E_INVALID, "depth must be 1..4");
+    h->depth = depth;
+    return LBM_OK;
+}
+
+int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
+{
+    if (!h || !key) return fail(LBM_E_INVALID, "NULL argument");
+    if (!strcmp(key, "wave_chunk")) {
+        if (value < 16 || value > (1 << 20)) return fail(LBM_E_INVALID, "wave_chunk must be in [16, 2^20]");
+        h->wave_chunk = (int)value;
+    } else if (!strcmp(key, "wave_rows")) {
+        if (value != 64 && value != 128) return fail(LBM_E_INVALID, "wave_rows must be 64 or 128");
+        h->wave_rows = (int)value;
+        for (bool &b : h->wave_attr_set) b = false;
+    } else if (!strcmp(key, "pf_ahead")) {
+        if (value < 0 || value > (1 << 20)) return fail(LBM_E_INVALID, "pf_ahead must be in [0, 2^20]");
+        h->pf_ahead = (int)value;
+    } else return fail(LBM_E_INVALID, "unknown tuning key '%s'", key);
+    return LBM_OK;
 }
 
 int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)

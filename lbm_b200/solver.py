@@ -120,6 +120,17 @@ class Solver:
     def step2_columns(self, xa, xb, row1=0, row2=0):
         C.check(self._L.lbm_step2_columns(self._h, xa, xb, row1, row2))
 
+    def stepn_columns(self, xa, xb, rows):
+        """len(rows) = 2..4 consecutive updates of columns [xa, xb) in one wavefront launch."""
+        r = (C.c_i64 * len(rows))(*[int(x) for x in rows])
+        C.check(self._L.lbm_stepn_columns(self._h, xa, xb, len(rows), r))
+
+    def set_temporal_depth(self, depth):
+        C.check(self._L.lbm_set_temporal_depth(self._h, int(depth)))
+
+    def set_tuning(self, key, value):
+        C.check(self._L.lbm_set_tuning(self._h, key.encode(), int(value)))
+
     def set_temporal_blocking(self, enable):
         C.check(self._L.lbm_set_temporal_blocking(self._h, int(enable)))
 

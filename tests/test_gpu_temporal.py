@@ -1,6 +1,7 @@
-"""GPU: the two-updates-per-launch kernel (temporal blocking) is bit-identical to two single
-updates, for every wall variant, odd sizes (tiles clipped, right wall first in its tile) and with
-time-dependent wall rows; strict arithmetic additionally equals the oracle bit for bit."""
+"""GPU: the multi-update launches (temporal blocking: step2_kernel with two updates per launch,
+stepw_kernel with up to four) are bit-identical to single updates, for every wall variant, odd
+sizes (tiles/strips/chunks clipped, right wall first in its tile) and with time-dependent wall
+rows; strict arithmetic additionally equals the oracle bit for bit."""
 import numpy as np
 import pytest
 
@@ -28,10 +29,13 @@ def _rows(nx, ny, n, seed, pressure):
     return rows
 
 
-def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False):
+def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False, depth=2, chunk=None):
     from lbm_b200.solver import Solver
     s = Solver(nx, ny, tau=0.58, arith=arith, dtype=dtype, right_wall=right)
     s.set_temporal_blocking(-1 if temporal else 0)
+    s.set_temporal_depth(depth)
+    if chunk:
+        s.set_tuning("wave_chunk", chunk)
     rng = np.random.default_rng(3)
     g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
          * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
@@ -59,18 +63,71 @@ def test_two_update_launch_equals_two_single_updates(nx, ny, right):
     assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
 
 
+@pytest.mark.parametrize("depth", [3, 4])
+@pytest.mark.parametrize("nx,ny", [(17, 70), (33, 64), (50, 130), (128, 128), (4, 5), (97, 300), (40, 121)])
+@pytest.mark.parametrize("right", ["velocity", "pressure"])
+def test_wavefront_launch_equals_single_updates(nx, ny, right, depth):
+    """stepw_kernel: 3 or 4 updates per launch; strips of 124 / 120 rows (ny = 121, 130, 300 span
+    several), chunks of 16 columns (nx > 16 spans several, nx = 17, 33, 97 leave a one-column rest that
+    the launcher has to widen)."""
+    n = 9
+    a, la, _ = _run(nx, ny, n, True, right, depth=depth, chunk=16)
+    b, lb, _ = _run(nx, ny, n, False, right)
+    assert lb == n and la == -(-n // depth)
+    assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
+
+
+def test_wavefront_default_chunk_and_remainders():
+    """Default chunk (512 columns) on a lattice wider than one chunk; 10 updates at depth 4 = 4 + 4 + 2."""
+    a, la, _ = _run(700, 40, 10, True, "velocity", depth=4)
+    b, lb, _ = _run(700, 40, 10, False, "velocity")
+    assert la == 3 and lb == 10
+    assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
+
+
+def test_wavefront_column_ranges_compose():
+    """lbm_stepn_columns on [0, w), [w, nx-w), [nx-w, nx) (the slab driver's edge/interior launches)
+    equals one launch over all columns."""
+    from lbm_b200.solver import Solver
+    nx, ny, w = 90, 150, 20
+    outs = []
+    for split in (False, True):
+        s = Solver(nx, ny, tau=0.58, arith="strict")
+        rng = np.random.default_rng(3)
+        g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
+             * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
+        s.set_populations(g)
+        s.set_walls(_rows(nx, ny, 4, 5, False))
+        s.set_temporal_blocking(0)
+        s.step(1)
+        s.set_tuning("wave_chunk", 16)
+        rows = [0, 1, 2, 3]
+        if split:
+            s.stepn_columns(0, w, rows)
+            s.stepn_columns(nx - w, nx, rows)
+            s.stepn_columns(w, nx - w, rows)
+        else:
+            s.stepn_columns(0, nx, rows)
+        s.flip()
+        outs.append(s.populations("post_collision"))
+        s.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("n", [6, 7])
 def test_macro_on_the_last_update(n):
-    a, _, ma = _run(40, 48, n, True, "velocity", macro_last=True)
-    b, _, mb = _run(40, 48, n, False, "velocity", macro_last=True)
-    assert np.array_equal(a, b)
-    assert np.array_equal(ma[0], mb[0]) and np.array_equal(ma[1], mb[1])
+    for depth in (2, 4):
+        a, _, ma = _run(40, 48, n, True, "velocity", macro_last=True, depth=depth)
+        b, _, mb = _run(40, 48, n, False, "velocity", macro_last=True)
+        assert np.array_equal(a, b)
+        assert np.array_equal(ma[0], mb[0]) and np.array_equal(ma[1], mb[1])
 
 
-def test_fused_and_f32_variants_agree_too():
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_fused_and_f32_variants_agree_too(depth):
     for kw in (dict(arith="fused"), dict(arith="fused", dtype="f32"), dict(arith="strict", dtype="f32")):
-        a, _, _ = _run(37, 90, 8, True, "pressure", **kw)
-        b, _, _ = _run(37, 90, 8, False, "pressure", **kw)
+        a, _, _ = _run(37, 140, 8, True, "pressure", depth=depth, chunk=16, **kw)
+        b, _, _ = _run(37, 140, 8, False, "pressure", **kw)
         assert np.array_equal(a, b), kw
 
 
@@ -91,30 +148,32 @@ def test_batched_cavity_against_oracle_bitwise():
         assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
 
 
-def test_full_size_two_update_launch_checksum():
-    """BASELINE config 5 size (32768 x 32768 f64, 154.6 GB): six updates with two-update launches and
-    with single-update launches leave bit-identical populations (compared through on-device
-    checksums; the oracle cannot hold this lattice)."""
+def test_full_size_multi_update_launch_checksum():
+    """BASELINE config 5 size (32768 x 32768 f64, 154.6 GB): eight updates with four-update launches,
+    with two-update launches and with single-update launches leave bit-identical populations
+    (compared through on-device checksums; the oracle cannot hold this lattice)."""
     import torch
     from lbm_b200.solver import Solver
     if torch.cuda.get_device_properties(0).total_memory < 170e9:
         pytest.skip("needs a 180 GB device")
     n = 32768
 
-    def run(temporal):
+    def run(depth):
         s = Solver(n, n, tau=0.56)
-        s.set_temporal_blocking(1 if temporal else 0)
+        s.set_temporal_blocking(1 if depth > 1 else 0)
+        s.set_temporal_depth(depth)
         s.init_equilibrium(1.0)
-        rows = np.zeros((6, s.row_len))
-        for k in range(6):
+        rows = np.zeros((8, s.row_len))
+        for k in range(8):
             rows[k, 4 * n:5 * n] = 0.1 * (1.0 - np.exp(-(k + 1.0) ** 2 / 8.0))
         s.set_walls(rows)
         s.step(1)
         l0 = s.launches
-        s.step(6, 0, 1)
+        s.step(8, 0, 1)
         s.sync()
         cur, _ = s.views()
-        v = cur[:, 2:-2, :]
+        hl = s.layout.halo
+        v = cur[:, hl:-hl, :n]
         sums = [float(v[q].sum(dtype=torch.float64)) for q in range(9)]
         bits = [int(v[q].view(torch.int64).sum()) for q in range(9)]      # wrap-around sum of the bit patterns
         edge = v[:, :, -1].clone().cpu().numpy(), v[:, 0, :].clone().cpu().numpy()
@@ -123,9 +182,11 @@ def test_full_size_two_update_launch_checksum():
         del cur, v
         torch.cuda.empty_cache()
         return sums, bits, edge, launches
-    a = run(True)
-    b = run(False)
-    assert a[3] == 3 and b[3] == 6
-    assert a[0] == b[0] and a[1] == b[1]
-    assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
-    assert abs(sum(a[0]) / n / n - 1.0) < 1e-6            # mean density stays ~1 over six updates
+    b = run(1)
+    assert b[3] == 8
+    for depth, launches in ((4, 2), (2, 4)):
+        a = run(depth)
+        assert a[3] == launches
+        assert a[0] == b[0] and a[1] == b[1], depth
+        assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1]), depth
+    assert abs(sum(b[0]) / n / n - 1.0) < 1e-6            # mean density stays ~1 over eight updates
