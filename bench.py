@@ -193,19 +193,12 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, K, W = args.nx, args.ny, args.steps, args.warmup
     s = SlabSolver(nx, ny, TAU, dist, rank, world, local, dtype=args.dtype, overlap=not args.no_overlap)
-    temporal = not args.no_temporal
-    depth = 2 if temporal else 1
+    depth = 1 if args.no_temporal else max(1, min(4, args.depth))
+    temporal = depth > 1
 
     def advance(first_row, n):
-        """n lattice updates; with temporal blocking consecutive updates are paired into one launch."""
-        k = 0
-        while k < n:
-            if temporal and k + 1 < n:
-                s.update2(first_row + k, first_row + k + 1, next_depth=depth)
-                k += 2
-            else:
-                s.update(first_row + k, next_depth=depth)
-                k += 1
+        """n lattice updates, up to `depth` consecutive ones per launch (temporal blocking)."""
+        s.advance(first_row, n, depth)
     dev = torch.device("cuda", local)
 
     def barrier():
@@ -271,15 +264,12 @@ def gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    per = 2 if temporal else 1               # updates per launch = per e2e step
+    per = depth                              # updates per launch = per e2e step
     it = 0
     while it < Ke:
         m = min(per, Ke - it)
         s.set_walls(pinned[it:it + m])
-        if m == 2:
-            s.update2(0, 1, next_depth=depth)
-        else:
-            s.update(0, next_depth=depth)
+        s.advance(0, m, depth)
         s.finish()
         line_y = s.s.probe_line(1, ymid, m - 1)             # row y = ny/2, this slab's columns
         d2h = line_y.nbytes
@@ -296,9 +286,14 @@ def gpu_arm(args):
 
     # algorithmic bytes: one read + one write of the nine populations per cell and LAUNCH; a
     # two-update launch (temporal blocking) serves two lattice updates with them.
-    upl = 2 if (temporal and K >= 2) else 1
+    upl = min(depth, K)
     bpl = BYTES_PER_LUP[args.dtype] / upl
     peak, peak_src = measured_peak()
+    kname = {1: "step", 2: "step2"}.get(upl, "stepw%d" % upl)
+    kdesc = {1: "lbm::step_kernel<%s,fused>",
+             2: "lbm::step2_kernel<%s,fused,8,64> (two updates per launch; the populations cross HBM once per launch)"}.get(
+        upl, "lbm::stepw_kernel<%%s,fused,%d,64> (%d updates per launch, wavefront temporal blocking; the populations "
+             "cross HBM once per launch; FP64-issue bound, not HBM bound)" % (upl, upl))
     achieved = bpl * s.nxl * ny / (ms / K * 1e-3) / 1e9      # this rank's kernel: bytes per launch / duration
     out = {"metric": "MLUPS (%s)" % args.dtype, "value": value, "unit": "MLUPS", "n_gpus": world,
            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
@@ -308,7 +303,8 @@ def gpu_arm(args):
                       "parallelism": "slab%d" % world, "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed"
                                   % (2 * 9 * s.nxl * ny * (8 if args.dtype == "f64" else 4) / 1e9),
                       "halo_overlap": bool(s.overlap),
-                      "temporal_blocking": "2 updates per launch (step2_kernel)" if temporal else "off"},
+                      "temporal_blocking": ("%d updates per launch (%s)" % (depth, "step2_kernel" if depth == 2 else "stepw_kernel"))
+                                           if temporal else "off"},
            "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "updates_per_step": per,
                    "note": "per launch (%d update(s)): pinned-host wall profiles -> device, the update(s), centre-line "
@@ -316,10 +312,11 @@ def gpu_arm(args):
                            "reference's in-place time stepping" % per},
            "gpu_launches": launches,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": profiled_traffic(nx, ny, args.dtype, world, "step2" if temporal else "step"), "peak_source": peak_src,
+                        "traffic": profiled_traffic(nx, ny, args.dtype, world, kname), "peak_source": peak_src,
                         "bytes_per_lattice_update": bpl, "updates_per_launch": upl,
-                        "bytes_per_launch": BYTES_PER_LUP[args.dtype] * s.nxl * ny, "kernel": ("lbm::step2_kernel<%s,fused,8,64> (two updates per launch; the populations cross HBM once per launch)"
-                                   if temporal else "lbm::step_kernel<%s,fused>") % args.dtype,
+                        "bytes_per_launch": BYTES_PER_LUP[args.dtype] * s.nxl * ny, "kernel": kdesc % args.dtype,
+                        "single_update_roofline_mlups": peak * 1e3 / BYTES_PER_LUP[args.dtype],
+                        "value_over_single_update_roofline": value / world / (peak * 1e3 / BYTES_PER_LUP[args.dtype]),
                         "per": "rank 0 slab, bytes per launch / (timed region / launches)"},
            "clocks": clocks}
     if rank == 0:
@@ -347,6 +344,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-temporal", action="store_true")
+    ap.add_argument("--depth", type=int, default=4, help="lattice updates per launch (1, 2 = step2_kernel, 3/4 = stepw_kernel)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -26,6 +26,7 @@ template <> struct Ar<double, true> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double rcp(double b) { return __ddiv_rn(1.0, b); }   // (collide_fused is never strict)
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ void div2(double a0, double a1, double b, double &q0, double &q1)
     {
@@ -38,6 +39,7 @@ template <> struct Ar<float, true> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float rcp(float b) { return __fdiv_rn(1.0f, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
     static __device__ __forceinline__ void div2(float a0, float a1, float b, float &q0, float &q1)
     {
@@ -46,22 +48,20 @@ template <> struct Ar<float, true> {
     }
 };
 // FUSED division: the IEEE double division of nvcc is a ~60-instruction subroutine call, and the
-// update kernels are instruction-issue bound once the HBM traffic is halved (profiles/README.md).
-// The divisor is always a density or 1 +- u (normal range, far from 0/inf), so a reciprocal seed
-// (MUFU.RCP64H) refined by three Newton steps is used (single quotients add a residual correction):
-// no special-case handling, result within 1 ulp of the correctly rounded quotient.  (The
-// reference's Numba kernels run with fastmath, which licenses the same reciprocal rewrite.)
+// multi-update kernels are bound by FP64 issue and dependent-issue latency once the HBM traffic is
+// cut (profiles/README.md).  The divisor is always a density or 1 +- u (normal range, far from
+// 0/inf), so a reciprocal seed (MUFU.RCP64H, relative error < 1e-6 measured on B200 with
+// tools/probe/rcp_seed.cu) refined by ONE cubic step  y (1 + e + e^2),  e = 1 - b y  is used: three
+// dependent DFMAs, no special-case handling, |y b - 1| <= 2.3e-16 (measured over [1e-3, 1e3]).
+// Single quotients (wall cells) add a residual correction.  (The reference's Numba kernels run with
+// fastmath, which licenses the same reciprocal rewrite.)
 __device__ __forceinline__ double rcp_fast(double b)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
-    // the seed (MUFU.RCP64H) is good to ~8 bits: three quadratic steps -> 2^-64
-    double e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-b, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-b, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 __device__ __forceinline__ double mul_rcp(double a, double b, double y /* ~1/b */)
 {
@@ -73,10 +73,11 @@ template <> struct Ar<double, false> {
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double rcp(double b) { return rcp_fast(b); }
     static __device__ __forceinline__ double div(double a, double b) { return mul_rcp(a, b, rcp_fast(b)); }
     static __device__ __forceinline__ void div2(double a0, double a1, double b, double &q0, double &q1)
     {
-        const double y = rcp_fast(b);   // |y b - 1| <= ~1 ulp: the two quotients are good to 1.5 ulp
+        const double y = rcp_fast(b);   // |y b - 1| <= 2 ulp: the two quotients are good to 2.5 ulp
         q0 = a0 * y;
         q1 = a1 * y;
     }
@@ -86,6 +87,7 @@ template <> struct Ar<float, false> {
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float rcp(float b) { return __frcp_rn(b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
     static __device__ __forceinline__ void div2(float a0, float a1, float b, float &q0, float &q1)
     {
@@ -117,9 +119,13 @@ template <typename T> struct Coef {
 template <typename A, typename T>
 __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr)
 {
-    r = A::add(G[0], G[1]);
+    if (A::strict) {
+        r = A::add(G[0], G[1]);
 #pragma unroll
-    for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
+        for (int q = 2; q < 9; q++) r = A::add(r, G[q]);
+    } else {   // same sum as a tree: 4 dependent additions instead of 8 (the kernels are latency bound)
+        r = (((G[0] + G[1]) + (G[2] + G[3])) + ((G[4] + G[5]) + (G[6] + G[7]))) + G[8];
+    }
     dr = r;
     if (Stored<T>::dev) r = A::add(T(1.0), dr);
     T mx, my;
@@ -137,45 +143,57 @@ __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr
 // g_eq (nb.py:10-17) followed by the TRT collision (nb.py:25-35); G -> F in place.
 // Deviation storage: g_eq_q - w_q = w_q (dr + rho (t + t^2/2 - v)); the TRT combination has
 // coefficients a_self - a_opp + a_eq + a_opp = 1 and w_q = w_qbar, so it maps h to h unchanged.
-// FUSED arithmetic: the same collision written in the symmetric / antisymmetric parts of the
-// equilibrium.  With  eq_s = (geq_q + geq_qbar)/2 = w r (1 + 4.5 s^2 - v),  eq_a = (geq_q - geq_qbar)/2
-// = 3 w r s  (s = c_q.u)  and  a_eq + a_opp = om_p,  a_eq - a_opp = om_m  the TRT update of a pair is
+//
+// FUSED arithmetic (collide_fused): lattice.macro + nb_equilibrium + the TRT collision in one
+// expression tree, written in the MOMENTS  rho, m = rho u  and the symmetric / antisymmetric parts of
+// the equilibrium.  With  eq_s = (geq_q + geq_qbar)/2 = w rho (1 + 4.5 s^2 - v),  eq_a = (geq_q -
+// geq_qbar)/2 = 3 w rho s  (s = c_q.u, v = 1.5 u.u)  and  a_eq + a_opp = om_p,  a_eq - a_opp = om_m
+// the TRT update of a pair is
 //     F_q    = a_self g_q    - a_opp g_qbar + om_p eq_s + om_m eq_a
 //     F_qbar = a_self g_qbar - a_opp g_q    + om_p eq_s - om_m eq_a
-// 9 FP64 instructions per pair instead of 19 (the update kernels are FP64-issue and power bound once
-// the HBM traffic is halved).  Algebraically identical to nb.py:10-17 + 25-35; rounding differs at the
-// 1e-16 level like any FMA contraction does.  Deviation storage (f32): eq_s - w = w (dr + r (4.5 s^2 - v)).
-template <typename T>
-__device__ __forceinline__ void collide_fused(T (&G)[9], T r, T dr, T ux, T uy, const Coef<T> &c)
+// and, with  m_s = c_q.m = rho s  and  y = 1/rho,
+//     om_p eq_s = om_p w rho + y (4.5 om_p w m_s^2 - 1.5 om_p w m.m),      om_m eq_a = 3 om_m w m_s .
+// Everything except the last multiply-add by y is independent of the reciprocal: the dependent chain
+// of a cell is  9 loads -> 4 additions -> seed + 3 FMAs -> 1 FMA  (the multi-update kernels are bound
+// by FP64 dependent-issue latency, profiles/README.md), 74 FP64 instructions in all.  Algebraically
+// identical to lattice.py:181-189 + nb.py:10-17 + 25-35; rounding differs at the 1e-16 level like any
+// FMA contraction does.  Deviation storage (f32): om_p (eq_s - w) = om_p w dr + y (...), same form.
+template <typename A, typename T>
+__device__ __forceinline__ void collide_fused(T (&G)[9], const Coef<T> &c, bool want_u, T &r, T &ux, T &uy)
 {
     constexpr bool dev = Stored<T>::dev;
-    const T v = T(1.5) * (ux * ux + uy * uy);
-    const T rp0 = r * c.wp0, rp1 = r * c.wp1, rp5 = r * c.wp5;     // om_p w r
-    const T rq1 = r * c.wq1, rq5 = r * c.wq5;                      // 4.5 om_p w r
-    const T rm1 = r * c.wm1, rm5 = r * c.wm5;                      // 3 om_m w r
-    const T b0 = dev ? c.wp0 * dr - rp0 * v : rp0 - rp0 * v;       // om_p eq_s at s = 0
-    const T b1 = dev ? c.wp1 * dr - rp1 * v : rp1 - rp1 * v;
-    const T b5 = dev ? c.wp5 * dr - rp5 * v : rp5 - rp5 * v;
-    G[0] = c.one_m_omp * G[0] + b0;
-    const T s[4] = {ux, uy, ux + uy, uy - ux};
+    const T sum = (((G[0] + G[1]) + (G[2] + G[3])) + ((G[4] + G[5]) + (G[6] + G[7]))) + G[8];
+    r = dev ? T(1.0) + sum : sum;
+    const T d56 = G[5] - G[6], d78 = G[7] - G[8];
+    const T mx = ((G[1] - G[2]) + d56) - d78;
+    const T my = ((G[3] - G[4]) + d56) + d78;
+    const T y = A::rcp(r);
+    const T ms[4] = {mx, my, mx + my, my - mx};
+    const T h = T(1.5) * (mx * mx + my * my);
+    const T rp0 = sum * c.wp0, rp1 = sum * c.wp1, rp5 = sum * c.wp5;    // om_p w rho  (f32: om_p w dr)
+    const T hp0 = h * c.wp0, hp1 = h * c.wp1, hp5 = h * c.wp5;          // 1.5 om_p w m.m
+    G[0] = (c.one_m_omp * G[0] + rp0) - hp0 * y;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int q = 2 * k + 1, qb = q + 1;
-        const T P = (k < 2 ? rq1 : rq5) * (s[k] * s[k]) + (k < 2 ? b1 : b5);
-        const T M = (k < 2 ? rm1 : rm5) * s[k];
+        const T K = (k < 2 ? c.wq1 : c.wq5) * (ms[k] * ms[k]) - (k < 2 ? hp1 : hp5);
+        const T M = (k < 2 ? c.wm1 : c.wm5) * ms[k];
+        const T rp = k < 2 ? rp1 : rp5;
         const T gq = G[q], gb = G[qb];
-        G[q]  = c.a_self * gq + ((P + M) - c.a_opp * gb);
-        G[qb] = c.a_self * gb + ((P - M) - c.a_opp * gq);
+        const T bq = c.a_self * gq + ((rp + M) - c.a_opp * gb);
+        const T bb = c.a_self * gb + ((rp - M) - c.a_opp * gq);
+        G[q] = K * y + bq;
+        G[qb] = K * y + bb;
+    }
+    if (want_u) {   // lattice.macro's u, only where it is stored
+        ux = mx * y;
+        uy = my * y;
     }
 }
 
 template <typename A, typename T>
 __device__ __forceinline__ void collide(T (&G)[9], T r, T dr, T ux, T uy, const Coef<T> &c)
 {
-    if (!A::strict) {
-        collide_fused<T>(G, r, dr, ux, uy, c);
-        return;
-    }
     constexpr bool dev = Stored<T>::dev;
     const T w0 = T(4.0 / 9.0), w1 = T(1.0 / 9.0), w5 = T(1.0 / 36.0);
     const T v = A::mul(T(1.5), A::add(A::mul(ux, ux), A::mul(uy, uy)));
@@ -210,6 +228,20 @@ __device__ __forceinline__ void collide(T (&G)[9], T r, T dr, T ux, T uy, const 
                        A::mul(c.a_opp, eb));
         G[qb] = A::add(A::add(A::sub(A::mul(c.a_self, gb), A::mul(c.a_opp, gq)), A::mul(c.a_eq, eb)),
                        A::mul(c.a_opp, eq));
+    }
+}
+
+// macro + equilibrium + collision of one cell, G -> F in place; (r, ux, uy) are lattice.macro's
+// fields (ux, uy only if want_u).  STRICT: the reference's expression order; FUSED: collide_fused.
+template <typename A, typename T>
+__device__ __forceinline__ void collide_cell(T (&G)[9], const Coef<T> &c, bool want_u, T &r, T &ux, T &uy)
+{
+    if (A::strict) {
+        T dr;
+        macro<A, T>(G, r, ux, uy, dr);
+        collide<A, T>(G, r, dr, ux, uy, c);
+    } else {
+        collide_fused<A, T>(G, c, want_u, r, ux, uy);
     }
 }
 

@@ -144,14 +144,13 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
         }
     }
     if (MODE != kStreamOnly) {
-        T r, ux, uy, dr;
-        macro<A, T>(G, r, ux, uy, dr);
+        T r, ux, uy;
+        collide_cell<A, T>(G, p.coef, p.write_macro != 0, r, ux, uy);
         if (p.write_macro) {
             p.rho_out[idx] = r;
             p.u_out[idx] = ux;
             p.uy_out[idx] = uy;
         }
-        collide<A, T>(G, r, dr, ux, uy, p.coef);
     }
 #pragma unroll
     for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
@@ -309,9 +308,8 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            T r, ux, uy, dr;
-            macro<A, T>(G[k], r, ux, uy, dr);
-            collide<A, T>(G[k], r, dr, ux, uy, p.coef);
+            T r, ux, uy;
+            collide_cell<A, T>(G[k], p.coef, false, r, ux, uy);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -365,9 +363,8 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-            T r, ux, uy, dr;
-            macro<A, T>(G[k], r, ux, uy, dr);
-            collide<A, T>(G[k], r, dr, ux, uy, p.coef);
+            T r, ux, uy;
+            collide_cell<A, T>(G[k], p.coef, false, r, ux, uy);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -466,6 +463,20 @@ template <typename T, int ROWS, int COL> struct RingSource {
     }
 };
 
+// A cell on a wall (or one that shares its step with a deferred corner): the general per-cell
+// sequence, kept out of line so that the bulk path of stepw_kernel stays a straight run of
+// loads, arithmetic and stores (the two would otherwise be merged back into one by the compiler).
+template <typename A, typename T, typename Src>
+__device__ __noinline__ void wall_cell(const StepParams<T> &p, const T *walls, const Src &src, int xc, int y, T *out)
+{
+    T G[9], r, ux, uy;
+    src(xc, y, G);
+    apply_walls<A, T>(p, walls, src, xc, y, G, r, ux, uy);
+    collide_cell<A, T>(G, p.coef, false, r, ux, uy);
+#pragma unroll
+    for (int q = 0; q < 9; q++) out[q] = G[q];
+}
+
 template <typename T, bool STRICT, int D, int TYB, int R0, int MINB>
 __global__ void __launch_bounds__(D * TYB + 32, MINB)
 stepw_kernel(const __grid_constant__ StepParams<T> p)
@@ -523,10 +534,30 @@ stepw_kernel(const __grid_constant__ StepParams<T> p)
         return;
     }
 
-    const RingSource<T, ROWS, COL> src{(stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0,
-                                       stage == 0 ? R0 - 1 : R - 1, ys};
+    const T *const in_base = (stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0;
+    const int mask = stage == 0 ? R0 - 1 : R - 1;
+    const RingSource<T, ROWS, COL> src{in_base, mask, ys};
+    const T *const in_t = in_base + t;
     T *const out = lvl + stage * R * COL + M0 + t;           // own ring (stages 0 .. D-2)
     const T *const walls = p.wrow[stage];
+    const Coef<T> cf = p.coef;
+    // columns and rows whose cells see no wall (and no deferred corner): the bulk path
+    const int xi_lo = p.x_wl + 2, xi_hi = p.x_wr >= 0 ? p.x_wr : 0x7fffffff;
+    const bool inner_row = y > 0 && y < p.ny - 1;
+
+    auto store = [&](int xc, const T (&G)[9]) {
+        if (stage == D - 1) {
+            if (store_row) {
+                const int idx = xc * p.pitch + y;
+#pragma unroll
+                for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+            }
+        } else {
+            T *o = out + (xc & (R - 1)) * COL;
+#pragma unroll
+            for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
+        }
+    };
 
     for (int s = 0; s < nsteps; s++) {
         const int x = xs0 + s - LAG * stage;
@@ -536,27 +567,29 @@ stepw_kernel(const __grid_constant__ StepParams<T> p)
             const int c = x + 1;
             if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
         }
-        if (row_ok && x >= lo && x < hi) {
-            // left corners wait for the next column (see above); then two cells in one step
-            int n = 1, xc = x;
-            if (edge_row && x == p.x_wl) n = 0;
-            if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
-            for (; n > 0; n--, xc--) {
-                T G[9], r, ux, uy, dr;
-                src(xc, y, G);
-                apply_walls<A, T>(p, walls, src, xc, y, G, r, ux, uy);
-                macro<A, T>(G, r, ux, uy, dr);
-                collide<A, T>(G, r, dr, ux, uy, p.coef);
-                if (stage == D - 1) {
-                    if (store_row) {
-                        const int idx = xc * p.pitch + y;
+        if (x >= lo && x < hi) {
+            if (x >= xi_lo && x < xi_hi && inner_row) {
+                // bulk cell: pull, macro, collide, store -- nothing else
+                const T *c0 = in_t + (x & mask) * COL;
+                const T *cm = in_t + ((x - 1) & mask) * COL;
+                const T *cp = in_t + ((x + 1) & mask) * COL;
+                T G[9], r, ux, uy;
 #pragma unroll
-                        for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
-                    }
-                } else {
-                    T *o = out + (xc & (R - 1)) * COL;
-#pragma unroll
-                    for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
+                for (int q = 0; q < 9; q++) {
+                    const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
+                    G[q] = c[q * ROWS - cy_of(q)];
+                }
+                collide_cell<A, T>(G, cf, false, r, ux, uy);
+                store(x, G);
+            } else if (row_ok) {
+                // wall cells.  Left corners wait for the next column (see above); then two cells in one step
+                int n = 1, xc = x;
+                if (edge_row && x == p.x_wl) n = 0;
+                if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
+                for (; n > 0; n--, xc--) {
+                    T G[9];
+                    wall_cell<A, T>(p, walls, src, xc, y, G);
+                    store(xc, G);
                 }
             }
         }

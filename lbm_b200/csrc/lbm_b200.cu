@@ -58,7 +58,7 @@ struct lbm_handle {
     bool temporal = true;         // several updates per launch (step2_kernel / stepw_kernel) where possible
     int depth = 4;                // most updates per launch (lbm_set_temporal_depth)
     int wave_chunk = 512;         // columns swept by one block of stepw_kernel
-    int wave_rows = 128;          // rows of a strip of stepw_kernel (128, or 64 with two blocks per SM)
+    int wave_rows = 64;           // rows of a strip of stepw_kernel: 64 with two blocks per SM (measured faster), or 128 with one
     bool wave_attr_set[5] = {false, false, false, false, false};
     int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
     bool tb_force = false;        // pair updates even on small lattices (tests)

@@ -34,13 +34,38 @@ def slab_bounds(nx, world, rank):
 # of DESIGN.md).  Entries: (my column counted from the interface, populations, its halo depth).
 _PLAN1 = {"right": [(0, Q_RIGHT)], "left": [(0, Q_LEFT)]}
 _PLAN2 = {"right": [(0, (0, 3, 4) + Q_RIGHT), (1, Q_RIGHT)], "left": [(0, (0, 3, 4) + Q_LEFT), (1, Q_LEFT)]}
+_ALL = tuple(range(9))
+
+
+def _plan(depth):
+    """depth >= 3 (wavefront launches): the neighbour recomputes depth-1 updates on my edge columns and
+    streams whole columns in (TMA bulk copies of all nine planes), so it gets my last `depth` columns
+    complete.  (Column d only needs the populations that can still reach the interface in depth-d
+    steps; sending all nine keeps the copies contiguous and costs 9.4 MB per side at ny = 32768.)"""
+    if depth == 1:
+        return _PLAN1
+    if depth == 2:
+        return _PLAN2
+    return None     # handled as blocks of `depth` consecutive columns per plane (exchange_ops)
 
 
 def exchange_ops(view, nxl, rank, world, dist, halo=1, depth=1):
     """P2P ops that fill the halo columns of `view` ([9, nxl+2*halo, pitch], column index = x + halo)
-    for the next launch: depth 1 = single update, depth 2 = two-update launch."""
-    plan = _PLAN1 if depth == 1 else _PLAN2
+    for the next launch: depth 1 = single update, depth 2 = two-update launch, 3/4 = wavefront launch."""
+    plan = _plan(depth)
     ops = []
+    if plan is None:
+        # [q][x][y] keeps the `depth` edge columns of one plane contiguous: one message per plane
+        d = depth
+        if rank + 1 < world:
+            for q in range(9):
+                ops.append(dist.P2POp(dist.isend, view[q, halo + nxl - d:halo + nxl], rank + 1))
+                ops.append(dist.P2POp(dist.irecv, view[q, halo + nxl:halo + nxl + d], rank + 1))
+        if rank > 0:
+            for q in range(9):
+                ops.append(dist.P2POp(dist.isend, view[q, halo:halo + d], rank - 1))
+                ops.append(dist.P2POp(dist.irecv, view[q, halo - d:halo], rank - 1))
+        return ops
     if rank + 1 < world:
         for d, qs in plan["right"]:
             for q in qs:
@@ -77,9 +102,13 @@ class SlabSolver:
         self.nx, self.ny = nx, ny
         self.x0, self.nxl = slab_bounds(nx, world, rank)
         self.compute = torch.cuda.Stream(device=device)
-        self.comm = torch.cuda.Stream(device=device)
+        # the halo exchange must not queue behind the thousands of pending blocks of the interior
+        # launch: high-priority stream, its kernels take the next free SM slots
+        self.comm = torch.cuda.Stream(device=device, priority=-1)
         self.s = Solver(nx, ny, tau=tau, dtype=dtype, arith=arith, right_wall=right_wall,
                         device=device, x0=self.x0, nxl=self.nxl, stream=self.compute)
+        if world > 1 and self.nxl < self.s.layout.halo:
+            raise ValueError("slab of %d columns is narrower than the halo (%d)" % (self.nxl, self.s.layout.halo))
         self.overlap = overlap and world > 1 and self.nxl >= 4
         self._halo_ready = None
         self.edge = 16                   # columns of the edge launches of update2 (one tile)
@@ -150,6 +179,53 @@ class SlabSolver:
         self._exchange(oth, ev, next_depth)
         s.flip()
         self.updates += 2
+
+    def updaten(self, rows, next_depth=None):
+        """len(rows) = 2..4 lattice updates in one wavefront launch per column range."""
+        torch = self.torch
+        s, nxl = self.s, self.nxl
+        d = len(rows)
+        if next_depth is None:
+            next_depth = d
+        if self.world == 1:
+            s.stepn_columns(0, nxl, rows)
+            s.flip()
+            self.updates += d
+            return
+        if self._halo_ready is not None:
+            self.compute.wait_event(self._halo_ready)
+        _, oth = s.views()
+        ev = torch.cuda.Event()
+        w = self.edge
+        if self.overlap and nxl >= 4 * w:
+            s.stepn_columns(0, w, rows)
+            s.stepn_columns(nxl - w, nxl, rows)
+            ev.record(self.compute)
+            s.stepn_columns(w, nxl - w, rows)
+        else:
+            s.stepn_columns(0, nxl, rows)
+            ev.record(self.compute)
+        self._exchange(oth, ev, next_depth)
+        s.flip()
+        self.updates += d
+
+    def advance(self, first_row, n, depth, row_stride=1):
+        """n lattice updates starting with wall row first_row, at most `depth` per launch."""
+        k = 0
+        while k < n:
+            d = min(depth, n - k)
+            nxt = min(depth, n - k - d) or depth          # what the following launch will be
+            rows = [first_row + (k + j) * row_stride for j in range(d)]
+            if d >= 3:
+                self.updaten(rows, next_depth=nxt)
+            elif d == 2:
+                if depth > 2:
+                    self.updaten(rows, next_depth=nxt)
+                else:
+                    self.update2(rows[0], rows[1], next_depth=nxt)
+            else:
+                self.update(rows[0], next_depth=nxt)
+            k += d
 
     def finish(self):
         if self._halo_ready is not None:

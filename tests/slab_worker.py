@@ -17,7 +17,10 @@ def main():
     from lbm_b200.slab import SlabSolver
     from lbm_b200.solver import Solver
     nx, ny, n_upd, overlap = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4] == "1"
-    temporal = len(sys.argv) > 5 and sys.argv[5] == "1"
+    # updates per launch: 0 -> 1, 1 -> 2 (step2_kernel), 3 / 4 -> wavefront launches
+    tcode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    depth = {0: 1, 1: 2}.get(tcode, tcode)
+    temporal = depth > 1
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,16 +32,8 @@ def main():
     s = SlabSolver(nx, ny, tau, dist, rank, world, local, overlap=overlap)
     s.init_equilibrium(1.0)
     s.set_walls(rows)
-    depth = 2 if temporal else 1
     s.update(0, next_depth=depth)
-    it = 1
-    while it < n_upd:
-        if temporal and it + 1 < n_upd:
-            s.update2(it - 1, it, next_depth=depth)
-            it += 2
-        else:
-            s.update(it - 1, next_depth=depth)
-            it += 1
+    s.advance(0, n_upd - 1, depth)
     F = s.gather_populations()
     ok, err = True, 0.0
     if rank == 0:
@@ -51,7 +46,7 @@ def main():
         ref = one.populations("post_collision")
         ok = bool(np.array_equal(F, ref))
         err = float(np.max(np.abs(F - ref)))
-        print(json.dumps({"ok": ok, "max_abs_diff": err, "world": world, "overlap": overlap, "temporal": temporal,
+        print(json.dumps({"ok": ok, "max_abs_diff": err, "world": world, "overlap": overlap, "temporal": temporal, "depth": depth,
                           "checksum": float(np.sum(ref))}), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -15,7 +15,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("overlap,temporal", [(1, 0), (0, 0), (1, 1), (0, 1)])
+@pytest.mark.parametrize("overlap,temporal", [(1, 0), (0, 0), (1, 1), (0, 1), (1, 4), (0, 4), (1, 3)])
 def test_slab_equals_single_gpu(overlap, temporal):
     n = _ngpu()
     if n < 2:

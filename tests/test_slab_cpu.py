@@ -42,42 +42,43 @@ def _pull_interior(F):
     return G
 
 
-def _worker2(rank, world, port, nx, ny, out):
-    """Depth-2 exchange: after it, two consecutive pulls of the owned columns (the first one also on
-    the one-column rim, as step2_kernel does) equal two pulls of the undivided lattice."""
+def _worker2(rank, world, port, nx, ny, out, depth=2):
+    """Depth-d exchange: after it, d consecutive pulls of the owned columns (the earlier ones also on
+    the rim, as step2_kernel / stepw_kernel do) equal d pulls of the undivided lattice."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(11)
     F = rng.standard_normal((9, nx, ny))
     x0, nxl = slab.slab_bounds(nx, world, rank)
-    H, pitch = 2, ny + 5
+    H, pitch = max(2, depth), ny + 5
     view = torch.full((9, nxl + 2 * H, pitch), float("nan"), dtype=torch.float64)
     view[:, H:nxl + H, :ny] = torch.from_numpy(F[:, x0:x0 + nxl])
-    slab.exchange_halos(view, nxl, rank, world, dist, halo=H, depth=2)
-    local = view.numpy()[:, :, :ny]
-    G2 = _pull_interior(_pull_interior(local))[:, H:nxl + H]
-    ref = _pull_interior(_pull_interior(F))[:, x0:x0 + nxl]
+    slab.exchange_halos(view, nxl, rank, world, dist, halo=H, depth=depth)
+    G2, ref = view.numpy()[:, :, :ny], F
+    for _ in range(depth):
+        G2, ref = _pull_interior(G2), _pull_interior(ref)
+    G2, ref = G2[:, H:nxl + H], ref[:, x0:x0 + nxl]
     ok = True
     for x in range(nxl):
         gx = x0 + x
         for k in range(9):
-            if 0 <= gx - 2 * CX[k] < nx:
-                ok &= np.array_equal(G2[k, x, 2:ny - 2], ref[k, x, 2:ny - 2])
+            if 0 <= gx - depth * CX[k] < nx:
+                ok &= np.array_equal(G2[k, x, depth:ny - depth], ref[k, x, depth:ny - depth])
     out[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nx", [(2, 12), (3, 13)])
-def test_depth2_exchange_feeds_two_updates(world, nx):
+@pytest.mark.parametrize("world,nx,depth", [(2, 12, 2), (3, 13, 2), (2, 17, 4), (3, 19, 3)])
+def test_deep_exchange_feeds_several_updates(world, nx, depth):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker2, args=(world, port, nx, 11, out), nprocs=world, join=True)
+    mp.spawn(_worker2, args=(world, port, nx, 15, out, depth), nprocs=world, join=True)
     assert all(out[r] for r in range(world)) and len(out) == world
 
 
