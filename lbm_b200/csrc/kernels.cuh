@@ -386,18 +386,20 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
 // at sweep step s stage k computes update k+1 of column  xs0 + s - 2k  from the three columns
 // x-1, x, x+1 of the previous level and writes the result into its own ring of 4 columns in shared
 // memory (the last stage stores to global memory).  Level 0 -- the source populations -- is
-// streamed into an 8-column shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier) issued
-// by a dedicated producer warp five columns ahead of their use, so the compute threads never touch
-// global memory on the load side and never compute a global load address.
+// streamed into an 8-column shared-memory ring by TMA: one 3-D tensor copy (box = rows x 1 column x
+// 9 planes, cp.async.bulk.tensor + mbarrier) per column, issued by a producer warp five columns
+// ahead of its use, so the compute threads never touch global memory on the load side and never
+// compute a global load address; rows and columns outside the allocation are zero-filled by the
+// TMA unit.
 //
 //   * HBM traffic: one read + one write of the populations per D updates (144/D bytes per lattice
-//     update in f64), plus the re-read of the 2*M0 margin rows of each strip.
+//     update in f64), plus the margin rows of each strip (served by L2: neighbouring strips run
+//     side by side).
 //   * Redundant work: only along y.  A strip loses one row per side and update, so TYB rows yield
-//     TYB - 2*PAD output rows (PAD >= D-1, rounded to the 16-byte granularity of the bulk copies):
-//     128 -> 120 rows for D = 4 in f64, 6.7 % (the 8 x 64 tiles of step2_kernel recompute 14.5 %
-//     for D = 2).  Along x a chunk recomputes 2(D-1) columns per 512.
-//   * One __syncthreads per sweep step orders the ring traffic: stage k reads columns x-1..x+1 of
-//     level k-1 while stage k-1 writes column x+2 = slot (x-2) & 3.
+//     TO = TYB - 2(D-1) output rows: 64 -> 58 for D = 4 in f64, 10 % (the 8 x 64 tiles of
+//     step2_kernel recompute 14.5 % for D = 2).  Along x a chunk recomputes 2(D-1) columns per 512.
+//   * One block-wide barrier per sweep step orders the ring traffic: stage k reads columns
+//     x-1..x+1 of level k-1 while stage k-1 writes column x+2 = slot (x-2) & 3.
 //   * Same per-cell device functions as step_kernel, hence bit-identical results.
 //
 // Corner cells need the pulled populations of their x-neighbour on the horizontal wall
@@ -426,35 +428,46 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity
 {
     while (!mbar_try_wait(b, parity)) {}
 }
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *b)
+// TMA tile copy global -> shared of the box at (c0, c1, c2) of a 3-D tensor map; completion is
+// counted in bytes on an mbarrier (out-of-range elements are zero-filled and counted).
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0, int c1, int c2, unsigned long long *b)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(b)) : "memory");
 }
 
-template <typename T, int TYB> struct Wave {
-    static constexpr int M0 = 16 / (int)sizeof(T);      // bulk copies move multiples of 16 bytes
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), built by the host
+
+// Geometry of a strip.  The TMA unit wants the box to start on a 16-byte boundary along the
+// contiguous axis (measured: odd start rows trap in f64), i.e. the first loaded row ys - M0 =
+// strip * TO - PAD - M0 has to be a multiple of AL = 16 / sizeof(T) rows, and a box row has to fill
+// whole 16-byte units.  PAD rows are lost on each side of a strip (PAD >= D - 1).
+template <typename T, int TYB, int D> struct Wave {
+    static constexpr int AL = 16 / (int)sizeof(T);                       // rows per 16 bytes: 2 (f64), 4 (f32)
+    static constexpr int PAD = (D - 1 + AL / 2 - 1) / (AL / 2) * (AL / 2);   // multiple of AL/2 so that TO is a multiple of AL
+    static constexpr int M0 = AL - PAD % AL == AL && AL == 2 ? 2 : AL - PAD % AL;   // margin rows: PAD + M0 multiple of AL, M0 >= 1
+    static constexpr int TO = TYB - 2 * PAD;            // output rows of a strip
     static constexpr int ROWS = TYB + 2 * M0;           // rows of one plane-column in a ring: t = -M0 .. TYB+M0-1
     static constexpr int COL = 9 * ROWS;                // elements of one ring slot (a column of the strip)
+    static constexpr int COL0 = (COL * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);   // level 0: TMA wants 128-byte aligned slots
     static constexpr int R = 4;                         // slots of the rings between stages
     static constexpr int LAG = 2;                       // columns between consecutive stages
     static constexpr int HDR = 128;                     // mbarriers
-    __host__ __device__ static constexpr int pad(int D) { return (D - 1 + M0 - 1) / M0 * M0; }
-    __host__ __device__ static constexpr int out_rows(int D) { return TYB - 2 * pad(D); }
-    __host__ __device__ static constexpr size_t smem(int D, int R0) { return HDR + (size_t)(R0 + (D - 1) * R) * COL * sizeof(T); }
+    static constexpr size_t smem(int R0) { return HDR + ((size_t)R0 * COL0 + (size_t)(D - 1) * R * COL) * sizeof(T); }
+    static_assert(TO > 0 && TO % AL == 0 && (PAD + M0) % AL == 0 && M0 >= 1 && (2 * M0) % AL == 0, "strip geometry");
 };
 
-template <typename T, int ROWS, int COL> struct RingSource {
+template <typename T, int ROWS> struct RingSource {
     const T *base;          // (slot 0, q 0, row of t = 0)
     int mask;               // slots - 1
+    int stride;             // elements per slot
     int ys;                 // lattice y of t = 0
     __device__ __forceinline__ void operator()(int x, int y, T (&G)[9]) const
     {
         const int t = y - ys;
-        const T *c0 = base + (x & mask) * COL + t;
-        const T *cm = base + ((x - 1) & mask) * COL + t;    // column x-1 feeds the populations with c_x = +1
-        const T *cp = base + ((x + 1) & mask) * COL + t;
+        const T *c0 = base + (x & mask) * stride + t;
+        const T *cm = base + ((x - 1) & mask) * stride + t;    // column x-1 feeds the populations with c_x = +1
+        const T *cp = base + ((x + 1) & mask) * stride + t;
 #pragma unroll
         for (int q = 0; q < 9; q++) {
             const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
@@ -479,18 +492,18 @@ __device__ __noinline__ void wall_cell(const StepParams<T> &p, const T *walls, c
 
 template <typename T, bool STRICT, int D, int TYB, int R0, int MINB>
 __global__ void __launch_bounds__(D * TYB + 32, MINB)
-stepw_kernel(const __grid_constant__ StepParams<T> p)
+stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ TensorMap tmap)
 {
     using A = Ar<T, STRICT>;
-    using W = Wave<T, TYB>;
-    constexpr int M0 = W::M0, ROWS = W::ROWS, COL = W::COL, R = W::R, LAG = W::LAG;
-    constexpr int PAD = W::pad(D), TO = W::out_rows(D);
+    using W = Wave<T, TYB, D>;
+    constexpr int M0 = W::M0, ROWS = W::ROWS, COL = W::COL, COL0 = W::COL0, R = W::R, LAG = W::LAG;
+    constexpr int PAD = W::PAD, TO = W::TO;
     constexpr int NC = D * TYB, NT = NC + 32;            // compute threads + one producer warp
     static_assert(TO > 0 && (R0 & (R0 - 1)) == 0 && R0 >= 8, "bad wavefront geometry");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
-    T *lvl0 = reinterpret_cast<T *>(smem_raw + W::HDR);      // [R0][9][ROWS]   level 0 (TMA ring)
-    T *lvl = lvl0 + R0 * COL;                                // [D-1][R][9][ROWS] levels 1 .. D-1
+    extern __shared__ __align__(1024) unsigned char wave_smem[];
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wave_smem);
+    T *lvl0 = reinterpret_cast<T *>(wave_smem + W::HDR);     // [R0][COL0]         level 0 (TMA ring)
+    T *lvl = lvl0 + R0 * COL0;                               // [D-1][R][9][ROWS]  levels 1 .. D-1
 
     const int stage = threadIdx.x / TYB, t = threadIdx.x - stage * TYB;
     const int ys = (int)blockIdx.x * TO - PAD, y = ys + t;
@@ -498,21 +511,6 @@ stepw_kernel(const __grid_constant__ StepParams<T> p)
     const int xs0 = ca - (D - 1);                            // first column of stage 0
     const int c_first = xs0 - 2, c_last = cb + D - 1;        // level-0 columns that are loaded
     const int nsteps = (cb - ca) + 2 * (D - 1) + LAG * (D - 1);
-    // stage k computes columns [ca - (D-1-k), cb + (D-1-k)) that exist in the global lattice
-    const int lo = max(ca - (D - 1 - stage), p.x_lo), hi = min(cb + (D - 1 - stage), p.x_hi);
-    const bool row_ok = y >= 0 && y < p.ny;
-    const bool edge_row = y == 0 || y == p.ny - 1;
-    const bool store_row = t >= PAD && t < PAD + TO;
-
-    auto load_column = [&](int c) {                          // one thread: 9 bulk copies, one per plane
-        unsigned long long *b = mbar + (c & (R0 - 1));
-        mbar_expect_tx(b, 9u * ROWS * (unsigned)sizeof(T));
-        const int cc = min(max(c, -kHalo), p.nxl + kHalo - 1);     // stay inside the allocation
-        T *d = lvl0 + (c & (R0 - 1)) * COL;
-        const long long off = (long long)cc * p.pitch + (ys - M0);
-#pragma unroll
-        for (int q = 0; q < 9; q++) bulk_g2s(d + q * ROWS, p.ctr[q] + off, ROWS * (unsigned)sizeof(T), b);
-    };
 
     if (threadIdx.x == NC) {
         for (int i = 0; i < R0; i++) mbar_init(mbar + i, 1);
@@ -523,27 +521,38 @@ stepw_kernel(const __grid_constant__ StepParams<T> p)
 
     // ---- producer warp: one lane streams the level-0 columns in, five columns ahead of stage 0 ----
     if (threadIdx.x >= NC) {
+        auto load_column = [&](int c) {                      // tensor coordinates: (row, column + halo, plane)
+            unsigned long long *b = mbar + (c & (R0 - 1));
+            mbar_expect_tx(b, 9u * ROWS * (unsigned)sizeof(T));
+            tma_load_3d(lvl0 + (c & (R0 - 1)) * COL0, &tmap, ys - M0, c + kHalo, 0, b);
+        };
         if (threadIdx.x == NC)
             for (int c = c_first; c < c_first + R0 && c <= c_last; c++) load_column(c);
         for (int s = 0; s < nsteps; s++) {
             // the ring holds columns x-2 .. x+R0-3 of stage 0's column x = xs0 + s; x-3 was last read in step s-1
             if (threadIdx.x == NC && s >= 1 && xs0 + s + R0 - 3 <= c_last) load_column(xs0 + s + R0 - 3);
-            __syncwarp();
+            __syncwarp();                                    // (the barrier instruction wants the whole warp)
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
         return;
     }
 
+    // stage k computes columns [ca - (D-1-k), cb + (D-1-k)) that exist in the global lattice
+    const int lo = max(ca - (D - 1 - stage), p.x_lo), hi = min(cb + (D - 1 - stage), p.x_hi);
+    const bool row_ok = y >= 0 && y < p.ny;
+    const bool edge_row = y == 0 || y == p.ny - 1;
+    const bool store_row = t >= PAD && t < PAD + TO;
     const T *const in_base = (stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0;
-    const int mask = stage == 0 ? R0 - 1 : R - 1;
-    const RingSource<T, ROWS, COL> src{in_base, mask, ys};
+    const int mask = stage == 0 ? R0 - 1 : R - 1, stride = stage == 0 ? COL0 : COL;
+    const RingSource<T, ROWS> src{in_base, mask, stride, ys};
     const T *const in_t = in_base + t;
     T *const out = lvl + stage * R * COL + M0 + t;           // own ring (stages 0 .. D-2)
     const T *const walls = p.wrow[stage];
     const Coef<T> cf = p.coef;
-    // columns and rows whose cells see no wall (and no deferred corner): the bulk path
-    const int xi_lo = p.x_wl + 2, xi_hi = p.x_wr >= 0 ? p.x_wr : 0x7fffffff;
+    // columns whose cells see no wall and no deferred corner, for a row that is not a wall row: the bulk path
     const bool inner_row = y > 0 && y < p.ny - 1;
+    const int f_lo = inner_row ? max(lo, p.x_wl + 2) : 0x7fffffff;
+    const int f_n = inner_row ? max(min(hi, p.x_wr >= 0 ? p.x_wr : 0x7fffffff) - f_lo, 0) : 0;
 
     auto store = [&](int xc, const T (&G)[9]) {
         if (stage == D - 1) {
@@ -559,38 +568,36 @@ stepw_kernel(const __grid_constant__ StepParams<T> p)
         }
     };
 
-    for (int s = 0; s < nsteps; s++) {
-        const int x = xs0 + s - LAG * stage;
+    int x = xs0 - LAG * stage;
+    for (int s = 0; s < nsteps; s++, x++) {
         if (stage == 0) {
             if (s == 0)
                 for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
             const int c = x + 1;
             if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
         }
-        if (x >= lo && x < hi) {
-            if (x >= xi_lo && x < xi_hi && inner_row) {
-                // bulk cell: pull, macro, collide, store -- nothing else
-                const T *c0 = in_t + (x & mask) * COL;
-                const T *cm = in_t + ((x - 1) & mask) * COL;
-                const T *cp = in_t + ((x + 1) & mask) * COL;
-                T G[9], r, ux, uy;
+        if ((unsigned)(x - f_lo) < (unsigned)f_n) {
+            // bulk cell: pull, collide, store -- nothing else
+            const T *c0 = in_t + (x & mask) * stride;
+            const T *cm = in_t + ((x - 1) & mask) * stride;
+            const T *cp = in_t + ((x + 1) & mask) * stride;
+            T G[9], r, ux, uy;
 #pragma unroll
-                for (int q = 0; q < 9; q++) {
-                    const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
-                    G[q] = c[q * ROWS - cy_of(q)];
-                }
-                collide_cell<A, T>(G, cf, false, r, ux, uy);
-                store(x, G);
-            } else if (row_ok) {
-                // wall cells.  Left corners wait for the next column (see above); then two cells in one step
-                int n = 1, xc = x;
-                if (edge_row && x == p.x_wl) n = 0;
-                if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
-                for (; n > 0; n--, xc--) {
-                    T G[9];
-                    wall_cell<A, T>(p, walls, src, xc, y, G);
-                    store(xc, G);
-                }
+            for (int q = 0; q < 9; q++) {
+                const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
+                G[q] = c[q * ROWS - cy_of(q)];
+            }
+            collide_cell<A, T>(G, cf, false, r, ux, uy);
+            store(x, G);
+        } else if (row_ok && x >= lo && x < hi) {
+            // wall cells.  Left corners wait for the next column (see above); then two cells in one step
+            int n = 1, xc = x;
+            if (edge_row && x == p.x_wl) n = 0;
+            if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
+            for (; n > 0; n--, xc--) {
+                T G[9];
+                wall_cell<A, T>(p, walls, src, xc, y, G);
+                store(xc, G);
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");

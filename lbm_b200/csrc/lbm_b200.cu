@@ -3,6 +3,7 @@
 // One fused kernel per lattice update: pull-stream from the post-collision array F of the
 // previous update, obstacle (interpolated) bounce-back, Zou-He walls/corners, macro,
 // equilibrium, TRT collision, store.  See DESIGN.md for layout and roofline.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -60,6 +61,8 @@ struct lbm_handle {
     int wave_chunk = 512;         // columns swept by one block of stepw_kernel
     int wave_rows = 64;           // rows of a strip of stepw_kernel: 64 with two blocks per SM (measured faster), or 128 with one
     bool wave_attr_set[5] = {false, false, false, false, false};
+    TensorMap tmap[2];            // one 3-D tensor map per population buffer (stepw_kernel's TMA loads)
+    int tmap_rows = 0;            // strip geometry (rows, depth) the maps were built for (0 = not built)
     int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
     bool tb_force = false;        // pair updates even on small lattices (tests)
     bool smem_attr_set = false;
@@ -266,13 +269,50 @@ static int launch_step2(lbm_handle *h, int src, int dst, int xa, int xb, int64_t
 }
 
 
+
+// ---- TMA tensor maps of the population buffers (stepw_kernel) -----------------------------
+// 3-D tensor (row y, column x + halo, plane q) over one buffer; box = ROWS rows x 1 column x 9
+// planes = one ring slot.  cuTensorMapEncodeTiled comes from the driver through the runtime's
+// entry-point query, so the library does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ensure_tensor_maps(lbm_handle *h, int rows_per_slot, int key /* strip rows and depth */)
+{
+    const int tyb = key;
+    if (h->tmap_rows == tyb) return LBM_OK;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(LBM_E_UNSUPPORTED, "driver has no cuTensorMapEncodeTiled");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    static_assert(sizeof(TensorMap) == sizeof(CUtensorMap), "TensorMap must mirror CUtensorMap");
+    const cuuint64_t dims[3] = {(cuuint64_t)h->lay.pitch, (cuuint64_t)(h->cfg.nxl + 2 * kHalo), 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->lay.pitch * h->esz, (cuuint64_t)h->lay.plane * h->esz};
+    const cuuint32_t box[3] = {(cuuint32_t)rows_per_slot, 1, 9}, estr[3] = {1, 1, 1};
+    for (int b = 0; b < 2; b++) {
+        void *base = elem_ptr(h, b, -(int64_t)kHalo * h->lay.pitch);     // (q = 0, x = -halo, y = 0)
+        CUresult r = encode(reinterpret_cast<CUtensorMap *>(&h->tmap[b]),
+                            h->cfg.dtype == LBM_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                            3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    }
+    h->tmap_rows = tyb;
+    return LBM_OK;
+}
+
 // ---- wavefront temporal blocking: D updates per launch ----------------------------------
 constexpr int kWaveR0 = 8;
 
 template <typename T, bool STRICT, int D, int kWaveRows, int MINB>
 static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const int64_t *rows)
 {
-    using W = Wave<T, kWaveRows>;
+    using W = Wave<T, kWaveRows, D>;
     StepParams<T> p;
     LinkParams lp;
     fill_params<T>(h, p, lp, src, dst, xa, xb, rows[0], 0);
@@ -286,16 +326,18 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
     int chunk = std::max(16, h->wave_chunk);
     while (n > chunk && n % chunk == 1) chunk++;
     p.chunk = chunk;
-    constexpr size_t smem = W::smem(D, kWaveR0);
+    constexpr size_t smem = W::smem(kWaveR0);
+    int rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
+    if (rc) return rc;
     auto kern = stepw_kernel<T, STRICT, D, kWaveRows, kWaveR0, MINB>;
     if (!h->wave_attr_set[D]) {   // per handle: the attribute belongs to the handle's device
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->wave_attr_set[D] = true;
     }
-    constexpr int TO = W::out_rows(D);
+    constexpr int TO = W::TO;
     dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)((n + chunk - 1) / chunk)), block(D * kWaveRows + 32);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one wavefront launch");
-    kern<<<grid, block, smem, h->stream>>>(p);
+    kern<<<grid, block, smem, h->stream>>>(p, h->tmap[src]);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;
@@ -858,6 +900,7 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
     } else if (!strcmp(key, "wave_rows")) {
         if (value != 64 && value != 128) return fail(LBM_E_INVALID, "wave_rows must be 64 or 128");
         h->wave_rows = (int)value;
+        h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
     } else if (!strcmp(key, "pf_ahead")) {
         if (value < 0 || value > (1 << 20)) return fail(LBM_E_INVALID, "pf_ahead must be in [0, 2^20]");

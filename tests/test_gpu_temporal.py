@@ -29,13 +29,15 @@ def _rows(nx, ny, n, seed, pressure):
     return rows
 
 
-def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False, depth=2, chunk=None):
+def _run(nx, ny, n, temporal, right, arith="strict", dtype="f64", macro_last=False, depth=2, chunk=None, rows=None):
     from lbm_b200.solver import Solver
     s = Solver(nx, ny, tau=0.58, arith=arith, dtype=dtype, right_wall=right)
     s.set_temporal_blocking(-1 if temporal else 0)
     s.set_temporal_depth(depth)
     if chunk:
         s.set_tuning("wave_chunk", chunk)
+    if rows:
+        s.set_tuning("wave_rows", rows)
     rng = np.random.default_rng(3)
     g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
          * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
@@ -67,7 +69,7 @@ def test_two_update_launch_equals_two_single_updates(nx, ny, right):
 @pytest.mark.parametrize("nx,ny", [(17, 70), (33, 64), (50, 130), (128, 128), (4, 5), (97, 300), (40, 121)])
 @pytest.mark.parametrize("right", ["velocity", "pressure"])
 def test_wavefront_launch_equals_single_updates(nx, ny, right, depth):
-    """stepw_kernel: 3 or 4 updates per launch; strips of 124 / 120 rows (ny = 121, 130, 300 span
+    """stepw_kernel: 3 or 4 updates per launch; strips of 60 / 58 output rows (ny >= 64 spans
     several), chunks of 16 columns (nx > 16 spans several, nx = 17, 33, 97 leave a one-column rest that
     the launcher has to widen)."""
     n = 9
@@ -77,10 +79,12 @@ def test_wavefront_launch_equals_single_updates(nx, ny, right, depth):
     assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
 
 
-def test_wavefront_default_chunk_and_remainders():
-    """Default chunk (512 columns) on a lattice wider than one chunk; 10 updates at depth 4 = 4 + 4 + 2."""
-    a, la, _ = _run(700, 40, 10, True, "velocity", depth=4)
-    b, lb, _ = _run(700, 40, 10, False, "velocity")
+@pytest.mark.parametrize("rows", [64, 128])
+def test_wavefront_default_chunk_and_remainders(rows):
+    """Default chunk (512 columns) on a lattice wider than one chunk; 10 updates at depth 4 = 4 + 4 + 2;
+    both strip heights (64 rows at two blocks per SM, 128 rows at one)."""
+    a, la, _ = _run(700, 140, 10, True, "velocity", depth=4, rows=rows)
+    b, lb, _ = _run(700, 140, 10, False, "velocity")
     assert la == 3 and lb == 10
     assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
 
