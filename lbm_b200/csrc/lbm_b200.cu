@@ -59,8 +59,11 @@ struct lbm_handle {
     bool temporal = true;         // several updates per launch (step2_kernel / stepw_kernel) where possible
     int depth = 4;                // most updates per launch (lbm_set_temporal_depth)
     int wave_chunk = 512;         // columns swept by one block of stepw_kernel
+    bool wave_auto = true;        // balance the chunk count against the number of resident blocks
+    int n_sm = 148;               // SMs of the handle's device
     int wave_rows = 64;           // rows of a strip of stepw_kernel: 64 with two blocks per SM (measured faster), or 128 with one
     bool wave_attr_set[5] = {false, false, false, false, false};
+    int wave_occ[5] = {1, 1, 1, 1, 1};   // resident blocks per SM of stepw_kernel<.., D, ..>
     TensorMap tmap[2];            // one 3-D tensor map per population buffer (stepw_kernel's TMA loads)
     int tmap_rows = 0;            // strip geometry (rows, depth) the maps were built for (0 = not built)
     int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
@@ -320,20 +323,40 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
     // columns that exist in the global lattice; without a wall the slab continues into the halo
     p.x_lo = h->cfg.x0 == 0 ? 0 : -(1 << 20);
     p.x_hi = h->cfg.x0 + h->cfg.nxl == h->cfg.nx ? (int)h->cfg.nxl : (int)h->cfg.nxl + (1 << 20);
-    // chunks of columns; a right-wall corner reads its x-neighbour's pulled populations from the
-    // rings, so the chunk that holds the right wall must be at least two columns wide
+    // Chunks of columns.  wave_chunk (512) is the target: longer chunks amortise the 3(D-1) fill/drain
+    // steps of the stage pipeline, shorter ones give more blocks.  Blocks run ~0.3 ms each, so a launch
+    // of few waves (slabs at 4-8 GPUs) loses up to one wave at its tail: pick the chunk count near
+    // the target that fills the last wave best.  A right-wall corner reads its x-neighbour's pulled
+    // populations from the rings, so the chunk that holds the right wall must be at least two wide.
     const int n = xb - xa;
-    int chunk = std::max(16, h->wave_chunk);
-    while (n > chunk && n % chunk == 1) chunk++;
-    p.chunk = chunk;
+    constexpr int TOc = W::TO;
     constexpr size_t smem = W::smem(kWaveR0);
-    int rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
-    if (rc) return rc;
     auto kern = stepw_kernel<T, STRICT, D, kWaveRows, kWaveR0, MINB>;
     if (!h->wave_attr_set[D]) {   // per handle: the attribute belongs to the handle's device
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, D * kWaveRows + 32, smem));
+        h->wave_occ[D] = std::max(occ, 1);
         h->wave_attr_set[D] = true;
     }
+    const long long strips = (h->cfg.ny + TOc - 1) / TOc, slots = (long long)h->wave_occ[D] * h->n_sm;
+    int chunk = std::max(16, h->wave_chunk);
+    if (h->wave_auto && n > chunk) {
+        double best = 1e30;
+        const int target = chunk;
+        for (int nc = (n + target - 1) / target; nc <= std::max(1, 2 * n / target); nc++) {   // chunks of target/2 .. target columns
+            const int c = (n + nc - 1) / nc;
+            if (c < 64) break;
+            const long long blocks = strips * ((n + c - 1) / c);
+            const double waves = (double)blocks / slots;
+            const double cost = std::ceil(waves) / waves * (1.0 + 3.0 * (D - 1) / c);
+            if (cost < best - 1e-9) { best = cost; chunk = c; }
+        }
+    }
+    while (n > chunk && n % chunk == 1) chunk++;
+    p.chunk = chunk;
+    int rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
+    if (rc) return rc;
     constexpr int TO = W::TO;
     dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)((n + chunk - 1) / chunk)), block(D * kWaveRows + 32);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one wavefront launch");
@@ -440,6 +463,7 @@ int lbm_create(const lbm_cfg *cfg, lbm_t **out)
     compute_layout(*cfg, h->lay);
     h->esz = (size_t)h->lay.elem_size;
     h->row_len = 5 * cfg->ny + 4 * cfg->nx;
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     cudaError_t e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) { delete h; return fail(LBM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
@@ -897,6 +921,7 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
     if (!strcmp(key, "wave_chunk")) {
         if (value < 16 || value > (1 << 20)) return fail(LBM_E_INVALID, "wave_chunk must be in [16, 2^20]");
         h->wave_chunk = (int)value;
+        h->wave_auto = false;                   // an explicit chunk is taken literally
     } else if (!strcmp(key, "wave_rows")) {
         if (value != 64 && value != 128) return fail(LBM_E_INVALID, "wave_rows must be 64 or 128");
         h->wave_rows = (int)value;

@@ -196,7 +196,7 @@ class SlabSolver:
             self.compute.wait_event(self._halo_ready)
         _, oth = s.views()
         ev = torch.cuda.Event()
-        w = self.edge
+        w = max(8, d)                    # edge launches: the columns the neighbour needs, little more
         if self.overlap and nxl >= 4 * w:
             s.stepn_columns(0, w, rows)
             s.stepn_columns(nxl - w, nxl, rows)
