@@ -334,6 +334,7 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
     auto kern = stepw_kernel<T, STRICT, D, kWaveRows, kWaveR0, MINB>;
     if (!h->wave_attr_set[D]) {   // per handle: the attribute belongs to the handle's device
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, D * kWaveRows + 32, smem));
         h->wave_occ[D] = std::max(occ, 1);
@@ -341,9 +342,13 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
     }
     const long long strips = (h->cfg.ny + TOc - 1) / TOc, slots = (long long)h->wave_occ[D] * h->n_sm;
     int chunk = std::max(16, h->wave_chunk);
-    if (h->wave_auto && n > chunk) {
+    if (h->wave_auto) {
+        // measured on B200 (f64, D = 4, GLUPS at chunk 128 / 256 / 512): 4096^2 93 / 83 / 66, 8192^2 - / 112 / 104,
+        // 32768^2 - / 127 / 128: short launches want short blocks
+        const long long cells = (long long)n * h->cfg.ny;
+        const int target = cells >= (1LL << 28) ? 512 : (cells >= (1LL << 26) ? 256 : 128);
+        chunk = target;
         double best = 1e30;
-        const int target = chunk;
         for (int nc = (n + target - 1) / target; nc <= std::max(1, 2 * n / target); nc++) {   // chunks of target/2 .. target columns
             const int c = (n + nc - 1) / nc;
             if (c < 64) break;
@@ -352,6 +357,7 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
             const double cost = std::ceil(waves) / waves * (1.0 + 3.0 * (D - 1) / c);
             if (cost < best - 1e-9) { best = cost; chunk = c; }
         }
+        chunk = std::min(chunk, std::max(n, 16));
     }
     while (n > chunk && n % chunk == 1) chunk++;
     p.chunk = chunk;
@@ -841,8 +847,12 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         // blocks per SM the single-update kernel is faster (small lattices are latency bound)
         const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * 148 || h->tb_force;
         if (h->temporal && big && mode == kFused && h->n_obs == 0 && plain >= 2 && h->cfg.nxl >= 4) {
-            const int d = (int)std::min<int64_t>(plain, h->depth);
-            if (d >= 3 || (d == 2 && h->depth > 2)) {
+            int d = (int)std::min<int64_t>(plain, h->depth);
+            // wavefront launches pay off from ~4096^2 cells per slab (measured: 4096^2 93 vs 81 GLUPS for
+            // step2_kernel, 4096 x 2048 the other way round); below that pairs of updates
+            const bool wave_ok = h->tb_force || h->cfg.nxl * h->cfg.ny >= (1LL << 24);
+            if (!wave_ok) d = std::min(d, 2);
+            if ((d >= 3 || (d == 2 && h->depth > 2)) && wave_ok) {
                 int64_t rows[4];
                 for (int k = 0; k < d; k++) rows[k] = first_row + (s + k) * row_stride;
                 rc = launch_stepw(h, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, d, rows);
