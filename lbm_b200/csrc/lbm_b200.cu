@@ -714,8 +714,8 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
             }
             if (i >= x0 && i < x0 + nxl) {
                 const int64_t il = ie - x0;
-                if (il < -1 || il > nxl)
-                    return fail(LBM_E_UNSUPPORTED, "link %lld: IBB stencil reaches beyond the one-column slab halo", (long long)k);
+                if (il < -2 || il > nxl + 1)   // (i, j) + 2 c_qbar at most: two of the kHalo halo columns
+                    return fail(LBM_E_UNSUPPORTED, "link %lld: IBB stencil reaches beyond the slab halo", (long long)k);
             }
         }
         if (i < x0 || i >= x0 + nxl) continue;  // owned by another slab

@@ -49,10 +49,12 @@ def _plan(depth):
     return None     # handled as blocks of `depth` consecutive columns per plane (exchange_ops)
 
 
-def exchange_ops(view, nxl, rank, world, dist, halo=1, depth=1):
+def exchange_ops(view, nxl, rank, world, dist, halo=1, depth=1, full=False):
     """P2P ops that fill the halo columns of `view` ([9, nxl+2*halo, pitch], column index = x + halo)
-    for the next launch: depth 1 = single update, depth 2 = two-update launch, 3/4 = wavefront launch."""
-    plan = _plan(depth)
+    for the next launch: depth 1 = single update, depth 2 = two-update launch, 3/4 = wavefront launch.
+    full: whole columns (all nine populations) at any depth -- interpolated bounce-back reads both
+    directions of a link up to two columns away (nb.py:98-104)."""
+    plan = None if full else _plan(depth)
     ops = []
     if plan is None:
         # [q][x][y] keeps the `depth` edge columns of one plane contiguous: one message per plane
@@ -83,8 +85,8 @@ def exchange_ops(view, nxl, rank, world, dist, halo=1, depth=1):
     return ops
 
 
-def exchange_halos(view, nxl, rank, world, dist, halo=1, depth=1):
-    ops = exchange_ops(view, nxl, rank, world, dist, halo, depth)
+def exchange_halos(view, nxl, rank, world, dist, halo=1, depth=1, full=False):
+    ops = exchange_ops(view, nxl, rank, world, dist, halo, depth, full)
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
@@ -113,6 +115,27 @@ class SlabSolver:
         self._halo_ready = None
         self.edge = 16                   # columns of the edge launches of update2 (one tile)
         self.updates = 0
+        self.n_obs = 0
+
+    def set_links(self, obstacles, use_ibb=True):
+        """Obstacle link lists (GLOBAL column indices, the reference's obstacle.boundary / .ibb): every
+        rank passes the whole list, the library keeps the links whose fluid node lies in its slab.
+        With obstacles an update is one launch over the whole slab (the link blocks ride along), the
+        halo exchange carries two whole columns (IBB stencil), and forces() sums the per-rank
+        momentum-exchange sums over the ranks (one small all-reduce)."""
+        self.s.set_links(obstacles, use_ibb)
+        self.n_obs = len(obstacles) if obstacles else 0
+
+    def forces(self, first, n):
+        """[n, n_obs, 2] momentum-exchange sums of update slots first..first+n-1, whole domain."""
+        torch = self.torch
+        self.finish()
+        f = self.s.forces(first, n)
+        if self.world > 1:
+            t = torch.from_numpy(f).to(self.s.device)
+            self.dist.all_reduce(t)
+            f = t.cpu().numpy()
+        return f
 
     def init_equilibrium(self, rho=1.0):
         self.s.init_equilibrium(rho)
@@ -124,17 +147,18 @@ class SlabSolver:
         torch = self.torch
         self.comm.wait_event(after)
         with torch.cuda.stream(self.comm):
-            exchange_halos(oth, self.nxl, self.rank, self.world, self.dist, self.s.layout.halo, depth)
+            exchange_halos(oth, self.nxl, self.rank, self.world, self.dist, self.s.layout.halo,
+                           max(depth, 2) if self.n_obs else depth, full=self.n_obs > 0)
             self._halo_ready = torch.cuda.Event()
             self._halo_ready.record(self.comm)
 
-    def update(self, row=0, next_depth=1):
+    def update(self, row=0, next_depth=1, slot=0):
         """One lattice update of the whole (distributed) domain; next_depth = 2 if the next launch is a
-        two-update one (it needs a deeper halo)."""
+        two-update one (it needs a deeper halo); slot = force slot of this update (obstacles)."""
         torch = self.torch
         s, nxl = self.s, self.nxl
         if self.world == 1:
-            s.step_columns(0, nxl, row)
+            s.step_columns(0, nxl, row, slot)
             s.flip()
             self.updates += 1
             return
@@ -142,7 +166,10 @@ class SlabSolver:
             self.compute.wait_event(self._halo_ready)       # halos of the current array have landed
         _, oth = s.views()
         ev = torch.cuda.Event()
-        if self.overlap:
+        if self.n_obs:
+            s.step_columns(0, nxl, row, slot)               # link blocks ride along with the whole slab
+            ev.record(self.compute)
+        elif self.overlap:
             s.step_columns(0, 2, row)
             s.step_columns(nxl - 2, nxl, row)
             ev.record(self.compute)

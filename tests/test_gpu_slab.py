@@ -29,3 +29,18 @@ def test_slab_equals_single_gpu(overlap, temporal):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(line)
     assert out["ok"] and out["max_abs_diff"] == 0.0 and out["world"] == world
+
+
+def test_slab_with_obstacle_across_the_interface():
+    """Multi-GPU obstacles: IBB cylinder straddling a slab interface."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29655",
+           os.path.join(ROOT, "tests", "slab_obs_worker.py"), "60"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"] and out["pop_equal"] and out["straddles"] and out["max_force_diff"] < 1e-12
