@@ -888,7 +888,9 @@ int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot
     if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
     const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
     if (mode == kFused) { rc = check_row(h, row); if (rc) return rc; }
-    return launch_step(h, mode, h->cur, h->cur ^ 1, (int)xa, (int)xb, row, slot, (flags & LBM_STEP_MACRO_LAST) != 0);
+    rc = launch_step(h, mode, h->cur, h->cur ^ 1, (int)xa, (int)xb, row, slot, (flags & LBM_STEP_MACRO_LAST) != 0);
+    if (!rc && mode == kFused && xa == 0 && xb == h->cfg.nxl) h->force_n = std::max<int64_t>(h->force_n, slot + 1);   // link blocks rode along
+    return rc;
 }
 
 int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2)

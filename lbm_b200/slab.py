@@ -137,8 +137,8 @@ class SlabSolver:
             f = t.cpu().numpy()
         return f
 
-    def init_equilibrium(self, rho=1.0):
-        self.s.init_equilibrium(rho)
+    def init_equilibrium(self, rho=1.0, ux=0.0, uy=0.0):
+        self.s.init_equilibrium(rho, ux, uy)
 
     def set_walls(self, rows):
         self.s.set_walls(rows)

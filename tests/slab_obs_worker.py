@@ -37,7 +37,7 @@ def main():
     s = SlabSolver(nx, ny, tau, dist, rank, world, local, right_wall="pressure")
     s.set_links(obstacles)
     straddles = bool((bnd[:, 0] < s.x0).any() and (bnd[:, 0] >= s.x0).any()) if rank == world // 2 else False
-    s.init_equilibrium(1.0)
+    s.init_equilibrium(1.0, 0.03, 0.0)                      # uniform flow: the cylinder feels a force from the first update
     s.set_walls(rows)
     s.update(0)                                             # iteration 0: collide only
     forces = []
@@ -53,7 +53,7 @@ def main():
         one = Solver(nx, ny, tau=tau, device=local, right_wall="pressure")
         one.set_temporal_blocking(False)
         one.set_links(obstacles)
-        one.init_equilibrium(1.0)
+        one.init_equilibrium(1.0, 0.03, 0.0)
         one.set_walls(rows)
         one.step(1)
         one.step(n_upd - 1, 0, 1)
