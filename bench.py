@@ -147,7 +147,7 @@ def cpu_sample(budget_s, steps_hint=None):
     n = 4096
     while n > 1024 and (steps_hint or 4) * n * n / (rate * 1e6) > budget_s:
         n //= 2
-    steps = steps_hint or max(2, min(50, int(budget_s * rate * 1e6 / (n * n))))
+    steps = steps_hint or max(2, min(400, int(budget_s * rate * 1e6 / (n * n))))
     return n, steps, cores
 
 

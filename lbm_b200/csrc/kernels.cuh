@@ -197,34 +197,41 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
         }
         if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
     }
-    // last block done: fixed-order reduction of the per-link terms, per obstacle
+    // last block done: fixed-order reduction of the per-link terms, per obstacle.  Warp w sums the links
+    // a + w*32 + lane + 256 k of the obstacle's range [a, b) (strided partial sums, then a shuffle
+    // tree), thread 0 adds the eight warp sums in warp order: no dependence on block scheduling, one
+    // barrier per pass of (up to) kObsPass obstacles instead of nine per obstacle.
+    constexpr int kObsPass = 16;
     __shared__ bool last;
-    __shared__ double red[2][kBlock];
+    __shared__ double red[kObsPass][kBlock / 32][2];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
     __syncthreads();
     if (!last) return;
     __threadfence();
-    for (int o = 0; o < lp.n_obs; o++) {
-        double fx = 0.0, fy = 0.0;
-        for (int k = lp.obs_off[o] + threadIdx.x; k < lp.obs_off[o + 1]; k += nthreads) {
-            fx += __ldcg(lp.link_f + 2 * k);
-            fy += __ldcg(lp.link_f + 2 * k + 1);
-        }
-        red[0][threadIdx.x] = fx;
-        red[1][threadIdx.x] = fy;
-        __syncthreads();
-        for (int s = nthreads / 2; s > 0; s >>= 1) {
-            if (threadIdx.x < s) {
-                red[0][threadIdx.x] += red[0][threadIdx.x + s];
-                red[1][threadIdx.x] += red[1][threadIdx.x + s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
+    for (int o0 = 0; o0 < lp.n_obs; o0 += kObsPass) {
+        const int no = min(kObsPass, lp.n_obs - o0);
+        for (int o = 0; o < no; o++) {
+            double fx = 0.0, fy = 0.0;
+            for (int k = lp.obs_off[o0 + o] + threadIdx.x; k < lp.obs_off[o0 + o + 1]; k += nthreads) {
+                fx += __ldcg(lp.link_f + 2 * k);
+                fy += __ldcg(lp.link_f + 2 * k + 1);
             }
-            __syncthreads();
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                fx += __shfl_xor_sync(0xffffffffu, fx, m);
+                fy += __shfl_xor_sync(0xffffffffu, fy, m);
+            }
+            if (lane == 0) { red[o][warp][0] = fx; red[o][warp][1] = fy; }
         }
-        if (threadIdx.x == 0) {
-            lp.forces[2 * o] = red[0][0];
-            lp.forces[2 * o + 1] = red[1][0];
+        __syncthreads();
+        if (threadIdx.x < 2 * no) {
+            const int o = threadIdx.x >> 1, c = threadIdx.x & 1;
+            double f = red[o][0][c];
+            for (int w = 1; w < nwarps; w++) f += red[o][w][c];
+            lp.forces[2 * (o0 + o) + c] = f;
         }
         __syncthreads();
     }

@@ -46,6 +46,8 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 enum StateKind { kNone = 0, kHaveG = 1, kHaveF = 2 };
+struct lbm_handle;
+static void invalidate_graphs(lbm_handle *h);   // captured launches hold pointers and launch shapes
 
 struct lbm_handle {
     lbm_cfg cfg;
@@ -90,6 +92,17 @@ struct lbm_handle {
     std::vector<double> force_const;   // f32 deviation storage: sum over an obstacle's owned links of 2 w_q c_q
     void *d_probe = nullptr;
     int64_t probe_cap = 0;
+    // CUDA graphs of whole lbm_step batches on small (launch-bound) lattices
+    struct StepGraph {
+        int64_t n = 0, first_row = 0, stride = 0;
+        uint32_t flags = 0;
+        int cur0 = 0, cur1 = 0;
+        int64_t launches = 0;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<StepGraph> graphs;
+    bool use_graph = true;
     // accounting
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -97,6 +110,15 @@ struct lbm_handle {
 };
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static void invalidate_graphs(lbm_handle *h)
+{
+    for (auto &g : h->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    h->graphs.clear();
+}
 
 static void compute_layout(const lbm_cfg &c, lbm_layout &l)
 {
@@ -149,6 +171,7 @@ static int ensure_state(lbm_handle *h)
 static int ensure_macro(lbm_handle *h)
 {
     if (h->rho) return LBM_OK;
+    invalidate_graphs(h);
     const size_t n = (size_t)h->cfg.nxl * h->lay.pitch * h->esz;
     CUDA_TRY(cudaMalloc(&h->rho, n));
     CUDA_TRY(cudaMalloc(&h->u, 2 * n));
@@ -161,6 +184,7 @@ static int ensure_forces(lbm_handle *h, int64_t n)
 {
     const int nobs = std::max(h->n_obs, 1);
     if (h->d_forces && h->force_cap >= n) return LBM_OK;
+    invalidate_graphs(h);
     if (h->d_forces) { CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->d_forces)); h->d_forces = nullptr; }
     const int64_t cap = std::max<int64_t>(n, 64);
     CUDA_TRY(cudaMalloc(&h->d_forces, (size_t)cap * nobs * 2 * sizeof(double)));
@@ -492,6 +516,7 @@ int lbm_destroy(lbm_t *h)
     if (!h) return LBM_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    invalidate_graphs(h);
     if (h->own_buf) { cudaFree(h->buf[0]); cudaFree(h->buf[1]); }
     if (h->walls) cudaFree(h->walls);
     if (h->rho) cudaFree(h->rho);
@@ -540,6 +565,7 @@ int lbm_set_stream(lbm_t *h, void *cuda_stream)
 {
     CHECK_H(h);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
+    invalidate_graphs(h);
     return LBM_OK;
 }
 
@@ -548,6 +574,7 @@ int lbm_set_right_wall(lbm_t *h, int32_t right_wall)
     CHECK_H(h);
     if (right_wall != LBM_RIGHT_VELOCITY && right_wall != LBM_RIGHT_PRESSURE) return fail(LBM_E_INVALID, "bad right_wall");
     h->cfg.right_wall = right_wall;
+    invalidate_graphs(h);
     return LBM_OK;
 }
 
@@ -675,6 +702,7 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     free_links(h);
+    invalidate_graphs(h);
     h->force_const.clear();
     if (h->d_forces) { cudaFree(h->d_forces); h->d_forces = nullptr; h->force_cap = 0; }
     if (n_obstacles <= 0) return LBM_OK;
@@ -793,6 +821,7 @@ int lbm_set_walls(lbm_t *h, int64_t n_rows, const double *rows_host)
     if (n_rows < 1 || !rows_host) return fail(LBM_E_INVALID, "need at least one wall row");
     if (n_rows > h->wall_cap) {
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+        invalidate_graphs(h);
         if (h->walls) CUDA_TRY(cudaFree(h->walls));
         h->walls = nullptr;
         h->wall_cap = 0;
@@ -819,23 +848,12 @@ static int check_row(lbm_handle *h, int64_t row)
     return LBM_OK;
 }
 
-int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride, uint32_t flags)
+}  // extern "C"
+
+// The launches of n_updates consecutive updates on the handle's stream (or into a stream capture).
+static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, int64_t row_stride, uint32_t flags)
 {
-    CHECK_H(h);
-    if (n_updates < 0) return fail(LBM_E_INVALID, "n_updates < 0");
-    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
-    if (n_updates == 0) return LBM_OK;
-    int rc = ensure_forces(h, n_updates);
-    if (rc) return rc;
-    if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
-    // validate the rows before enqueuing anything
-    for (int64_t s = 0; s < n_updates; s++) {
-        if (s == 0 && h->kind == kHaveG) continue;  // collide-only update uses no walls
-        rc = check_row(h, first_row + s * row_stride);
-        if (rc) return rc;
-        if (row_stride == 0) break;
-    }
-    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    int rc = LBM_OK;
     for (int64_t s = 0; s < n_updates; s++) {
         const bool last = s == n_updates - 1;
         const bool wm = last && (flags & LBM_STEP_MACRO_LAST);
@@ -869,6 +887,62 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         if (rc) return rc;
         h->cur ^= 1;
         h->kind = kHaveF;
+    }
+    return LBM_OK;
+}
+
+extern "C" {
+
+int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride, uint32_t flags)
+{
+    CHECK_H(h);
+    if (n_updates < 0) return fail(LBM_E_INVALID, "n_updates < 0");
+    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
+    if (n_updates == 0) return LBM_OK;
+    int rc = ensure_forces(h, n_updates);
+    if (rc) return rc;
+    if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
+    // validate the rows before enqueuing anything
+    for (int64_t s = 0; s < n_updates; s++) {
+        if (s == 0 && h->kind == kHaveG) continue;  // collide-only update uses no walls
+        rc = check_row(h, first_row + s * row_stride);
+        if (rc) return rc;
+        if (row_stride == 0) break;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    // Small lattices are launch bound (4 us per update at 200 x 200, profiles/README.md): a batch of
+    // updates is captured once into a CUDA graph and replayed (the wall table, force slots and
+    // population buffers keep their addresses; their contents are read when the graph runs).
+    const bool graph_ok = h->use_graph && h->stream != nullptr && h->kind == kHaveF && n_updates >= 16 &&
+                          h->cfg.nxl * h->cfg.ny <= (1LL << 22);
+    if (graph_ok) {
+        lbm_handle::StepGraph *g = nullptr;
+        for (auto &e : h->graphs)
+            if (e.n == n_updates && e.first_row == first_row && e.stride == row_stride && e.flags == flags && e.cur0 == h->cur) g = &e;
+        if (!g) {
+            if (h->graphs.size() >= 4) invalidate_graphs(h);
+            lbm_handle::StepGraph e;
+            e.n = n_updates; e.first_row = first_row; e.stride = row_stride; e.flags = flags; e.cur0 = h->cur;
+            const int64_t l0 = h->launches;
+            CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            rc = enqueue_updates(h, n_updates, first_row, row_stride, flags);
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &e.graph);
+            if (rc) { if (e.graph) cudaGraphDestroy(e.graph); h->cur = e.cur0; return rc; }
+            if (ce != cudaSuccess) { h->cur = e.cur0; return fail(LBM_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
+            ce = cudaGraphInstantiate(&e.exec, e.graph, 0);
+            if (ce != cudaSuccess) { cudaGraphDestroy(e.graph); h->cur = e.cur0; return fail(LBM_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+            e.cur1 = h->cur;
+            e.launches = h->launches - l0;
+            h->graphs.push_back(e);
+            g = &h->graphs.back();
+        } else {
+            h->cur = g->cur1;
+            h->launches += g->launches;
+        }
+        CUDA_TRY(cudaGraphLaunch(g->exec, h->stream));
+    } else {
+        rc = enqueue_updates(h, n_updates, first_row, row_stride, flags);
+        if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->ev_valid = true;
@@ -924,12 +998,15 @@ int lbm_set_temporal_depth(lbm_t *h, int32_t depth)
     if (!h) return fail(LBM_E_INVALID, "handle is NULL");
     if (depth < 1 || depth > 4) return fail(LBM_E_INVALID, "depth must be 1..4");
     h->depth = depth;
+    invalidate_graphs(h);
     return LBM_OK;
 }
 
 int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
 {
     if (!h || !key) return fail(LBM_E_INVALID, "NULL argument");
+    invalidate_graphs(h);
+    if (!strcmp(key, "graph")) { h->use_graph = value != 0; return LBM_OK; }
     if (!strcmp(key, "wave_chunk")) {
         if (value < 16 || value > (1 << 20)) return fail(LBM_E_INVALID, "wave_chunk must be in [16, 2^20]");
         h->wave_chunk = (int)value;
@@ -950,6 +1027,7 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable)
 {
     if (!h) return fail(LBM_E_INVALID, "handle is NULL");
     h->temporal = enable != 0;
+    invalidate_graphs(h);
     h->tb_force = enable < 0;                   // negative: also on lattices too small to profit (tests)
     if (enable < 0) enable = -enable;
     return LBM_OK;

@@ -143,7 +143,12 @@ class lattice:
         tdt = torch.float64 if self.dtype == "f64" else torch.float32
         dev = torch.device("cuda", self.device)
         self._buf = [torch.empty(lay.elems, dtype=tdt, device=dev) for _ in range(2)]
-        C.check(self._L.lbm_set_stream(h, C.c_vp(torch.cuda.current_stream(dev).cuda_stream)))
+        # a stream of its own (not the legacy default stream): batches of updates on these small
+        # lattices are replayed as CUDA graphs, and stream capture needs a real stream
+        self._stream = torch.cuda.current_stream(dev)
+        if self._stream.cuda_stream == 0:
+            self._stream = torch.cuda.Stream(device=dev)
+        C.check(self._L.lbm_set_stream(h, C.c_vp(self._stream.cuda_stream)))
         C.check(self._L.lbm_bind_state(h, C.c_vp(self._buf[0].data_ptr()), C.c_vp(self._buf[1].data_ptr()),
                                        lay.elems * lay.elem_size))
 

@@ -38,6 +38,8 @@ class Solver:
         tdt = torch.float64 if dtype == "f64" else torch.float32
         self.buffers = [torch.empty(lay.elems, dtype=tdt, device=self.device) for _ in range(2)]
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if s.cuda_stream == 0:           # legacy default stream: no stream capture (CUDA graphs of batches)
+            s = torch.cuda.Stream(device=self.device)
         self.stream = s
         C.check(self._L.lbm_set_stream(h, C.c_vp(s.cuda_stream)))
         C.check(self._L.lbm_bind_state(h, C.c_vp(self.buffers[0].data_ptr()),

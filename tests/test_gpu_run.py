@@ -114,3 +114,37 @@ def test_checkpoint_restart_continues_bit_for_bit(tmp_path):
     for k in ("g_up", "g", "rho", "u"):
         assert np.array_equal(getattr(lc, k), getattr(la, k)), k
     assert np.array_equal(np.array(cb.forces[-40:]), np.array(ca.forces[-40:]))
+
+
+def test_graph_replay_equals_plain_launches():
+    """Batches of >= 16 updates on small lattices are captured into a CUDA graph and replayed
+    (lbm_step); populations, stored drag/lift sums and the macro fields must not notice."""
+    import os
+    from lbm_b200.solver import Solver
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "run_turek30.npz"))
+    nx, ny, n = 160, 30, 40
+    res = []
+    for graph in (1, 0):
+        s = Solver(nx, ny, tau=0.62, right_wall="pressure")
+        s.set_tuning("graph", graph)
+        s.set_links([cases.Obstacle(z["boundary"], z["ibb"])])
+        s.init_equilibrium(1.0, 0.03, 0.0)
+        yy = np.linspace(0.0, 1.0, ny)
+        rows = np.zeros((n, s.row_len))
+        for k in range(n):
+            rows[k, 0:ny] = 0.03 * (1.0 + 0.01 * k) * 4.0 * yy * (1.0 - yy)
+            rows[k, 4 * ny + 4 * nx:] = 1.0
+        s.set_walls(rows)
+        s.step(1)
+        out = []
+        for rep in range(3):                       # the second and third call replay the cached graph
+            l0 = s.launches
+            s.step(n, 0, 1, macro_last=True)
+            assert s.launches - l0 == n
+            out.append((s.populations("post_collision"), s.forces(0, n), s.macro()))
+        res.append(out)
+        s.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
+    assert np.max(np.abs(res[0][-1][1])) > 1e-6
