@@ -223,7 +223,11 @@ class SlabSolver:
             self.compute.wait_event(self._halo_ready)
         _, oth = s.views()
         ev = torch.cuda.Event()
-        w = max(8, d)                    # edge launches: the columns the neighbour needs, little more
+        # edge launches first (the neighbour needs my last d columns), the exchange overlaps the interior.
+        # A launch pays 3(d-1) pipeline fill/drain steps per chunk whatever its width, so the edges are
+        # whole chunks of 256 columns where the slab is wide enough (8 columns cost 20 sweep steps, 256
+        # cost 268), and the exchange still has the long interior launch to hide behind.
+        w = 256 if nxl >= 2048 else max(8, d)
         if self.overlap and nxl >= 4 * w:
             s.stepn_columns(0, w, rows)
             s.stepn_columns(nxl - w, nxl, rows)
