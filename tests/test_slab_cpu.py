@@ -42,7 +42,7 @@ def _pull_interior(F):
     return G
 
 
-def _worker2(rank, world, port, nx, ny, out, depth=2):
+def _worker2(rank, world, port, nx, ny, out, depth=2, packed=False):
     """Depth-d exchange: after it, d consecutive pulls of the owned columns (the earlier ones also on
     the rim, as step2_kernel / stepw_kernel do) equal d pulls of the undivided lattice."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -54,7 +54,10 @@ def _worker2(rank, world, port, nx, ny, out, depth=2):
     H, pitch = max(2, depth), ny + 5
     view = torch.full((9, nxl + 2 * H, pitch), float("nan"), dtype=torch.float64)
     view[:, H:nxl + H, :ny] = torch.from_numpy(F[:, x0:x0 + nxl])
-    slab.exchange_halos(view, nxl, rank, world, dist, halo=H, depth=depth)
+    if packed:
+        slab.exchange_packed(view, nxl, rank, world, dist, H, depth, {})
+    else:
+        slab.exchange_halos(view, nxl, rank, world, dist, halo=H, depth=depth)
     G2, ref = view.numpy()[:, :, :ny], F
     for _ in range(depth):
         G2, ref = _pull_interior(G2), _pull_interior(ref)
@@ -70,15 +73,16 @@ def _worker2(rank, world, port, nx, ny, out, depth=2):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nx,depth", [(2, 12, 2), (3, 13, 2), (2, 17, 4), (3, 19, 3)])
-def test_deep_exchange_feeds_several_updates(world, nx, depth):
+@pytest.mark.parametrize("world,nx,depth,packed", [(2, 12, 2, False), (3, 13, 2, False), (2, 17, 4, False), (3, 19, 3, False),
+                                                   (2, 17, 4, True), (3, 19, 3, True), (3, 13, 2, True)])
+def test_deep_exchange_feeds_several_updates(world, nx, depth, packed):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker2, args=(world, port, nx, 15, out, depth), nprocs=world, join=True)
+    mp.spawn(_worker2, args=(world, port, nx, 15, out, depth, packed), nprocs=world, join=True)
     assert all(out[r] for r in range(world)) and len(out) == world
 
 
