@@ -302,7 +302,10 @@ def gpu_arm(args):
                                   % (nx, ny, args.dtype, TAU, world),
                       "parallelism": "slab%d" % world, "l2": "working set %.1f GB per GPU >> 126 MB L2, no flush needed"
                                   % (2 * 9 * s.nxl * ny * (8 if args.dtype == "f64" else 4) / 1e9),
-                      "halo_overlap": bool(s.overlap),
+                      "halo_overlap": bool(s.overlap and (depth <= 2 or s.overlap_wave)),
+                      "halo_exchange": "none (one GPU)" if world == 1 else (
+                          "NCCL send/recv of %d whole columns per side, one packed message per direction, after each launch" % depth
+                          if depth >= 3 else "NCCL send/recv of the populations crossing the interface, overlapped with the interior launch"),
                       "temporal_blocking": ("%d updates per launch (%s)" % (depth, "step2_kernel" if depth == 2 else "stepw_kernel"))
                                            if temporal else "off"},
            "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
