@@ -188,6 +188,12 @@ int lbm_get_populations(lbm_t *h, int32_t which, void *host);
  * overwrites of a later lbm_apply_bc): the composite the reference leaves in lattice.rho/u. */
 int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host);
 
+/* |u| of the stored macro fields, speed[nxl][ny] in the handle dtype, with -1 on the cells flagged in
+ * solid[nxl][ny] (NULL: no mask): the field plot_norm (lbm/src/plot/plot.py:9-16) draws, computed on
+ * the device so that an output step transfers one plane instead of three; equals
+ * sqrt(u[0]**2 + u[1]**2) of lbm_get_macro bit for bit. */
+int lbm_get_speed(lbm_t *h, const unsigned char *solid_host, void *speed_host);
+
 /* rho, ux, uy along one lattice line of the streamed + boundary-treated current populations,
  * i.e. what lattice.macro() (lattice.py:178-189) of the next iteration yields there; serves the
  * centre-line readers cavity.line_fields (cavity.py:110-133) and poiseuille.compute_error

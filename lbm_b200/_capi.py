@@ -71,6 +71,7 @@ SIGNATURES = {
     "lbm_forces_now": (ctypes.c_int, [c_vp, c_vp]),
     "lbm_get_populations": (ctypes.c_int, [c_vp, c_i32, c_vp]),
     "lbm_get_macro": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+"lbm_get_speed": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "lbm_probe_line": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp]),
     "lbm_launch_count": (c_i64, [c_vp]),
     "lbm_last_step_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),

@@ -640,6 +640,23 @@ probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n
     out[2 * n + k] = uy;
 }
 
+// |u| of the stored macro fields, -1 on masked (solid) cells: what plot_norm (lbm/src/plot/plot.py:9-16)
+// computes on the host from lattice.u and lattice.lattice; separately rounded operations, so the
+// result equals np.sqrt(u[0]**2 + u[1]**2) bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+speed_kernel(const T *ux, const T *uy, const unsigned char *solid, T *out, int pitch, int ny)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    if (y >= ny) return;
+    const long long c = (long long)blockIdx.y * pitch + y;
+    using A = Ar<T, true>;
+    const T v2 = A::add(A::mul(ux[c], ux[c]), A::mul(uy[c], uy[c]));
+    T v = sizeof(T) == 8 ? (T)__dsqrt_rn((double)v2) : (T)__fsqrt_rn((float)v2);
+    if (solid && solid[c]) v = T(-1.0);
+    out[c] = v;
+}
+
 // uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
 template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kBlock)

@@ -1145,6 +1145,41 @@ int lbm_get_macro(lbm_t *h, void *rho_host, void *u_host)
     return rc;
 }
 
+int lbm_get_speed(lbm_t *h, const unsigned char *solid_host, void *speed_host)
+{
+    CHECK_H(h);
+    if (!speed_host) return fail(LBM_E_INVALID, "speed_host is NULL");
+    if (!h->macro_valid || !h->u) return fail(LBM_E_STATE, "no macroscopic fields stored: run lbm_step with LBM_STEP_MACRO_LAST");
+    if (h->cfg.nxl > 65535) return fail(LBM_E_UNSUPPORTED, "lbm_get_speed: slab wider than 65535 columns");
+    const size_t cells = (size_t)h->cfg.nxl * h->lay.pitch;
+    void *d_out = nullptr;
+    unsigned char *d_solid = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, cells * h->esz));
+    int rc = LBM_OK;
+    if (solid_host) {
+        cudaError_t e = cudaMalloc(&d_solid, cells);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_solid, h->lay.pitch, solid_host, (size_t)h->cfg.ny, (size_t)h->cfg.ny,
+                                                     (size_t)h->cfg.nxl, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "lbm_get_speed: %s", cudaGetErrorString(e));
+    }
+    if (!rc) {
+        dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)h->cfg.nxl), block(kBlock);
+        const int pitch = (int)h->lay.pitch, ny = (int)h->cfg.ny;
+        if (h->cfg.dtype == LBM_F64)
+            speed_kernel<double><<<grid, block, 0, h->stream>>>((const double *)h->u, (const double *)h->u + cells, d_solid, (double *)d_out, pitch, ny);
+        else
+            speed_kernel<float><<<grid, block, 0, h->stream>>>((const float *)h->u, (const float *)h->u + cells, d_solid, (float *)d_out, pitch, ny);
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "speed_kernel: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = copy_field_d2h(h, d_out, (int64_t)cells, speed_host, 1);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (d_solid) cudaFree(d_solid);
+    return rc;
+}
+
 int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out_host)
 {
     CHECK_H(h);

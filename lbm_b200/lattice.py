@@ -252,6 +252,20 @@ class lattice:
         walls = self._state == "streamed" and len(self._bcs) > 0
         return self._macro_arrays(walls)
 
+    def speed(self):
+        """|u| with -1 on obstacle nodes -- the array plot_norm (plot.py:12-15) builds from lattice.u and
+        lattice.lattice -- computed on the device from the fields of the last macro(): one plane to the
+        host instead of three.  (After set_bc the wall rows of lattice.u carry the Zou-He values; use
+        lattice.u there.)"""
+        if self._state in ("fresh", "g"):
+            v = np.sqrt(self._u_host[0] ** 2 + self._u_host[1] ** 2)
+            v[np.where(self.lattice > 0.0)] = -1.0
+            return v
+        out = np.empty((self.nx, self.ny), dtype=self._np)
+        m = np.ascontiguousarray(self.lattice > 0.0, dtype=np.uint8)
+        C.check(self._L.lbm_get_speed(self._handle(), self._ptr(m), self._ptr(out)))
+        return out
+
     @property
     def rho(self):
         return self._fields()[0]

@@ -179,6 +179,13 @@ class Solver:
         C.check(self._L.lbm_get_macro(self._h, self._p(rho), self._p(u)))
         return rho, u
 
+    def speed(self, solid=None):
+        """|u| of the stored macro fields (-1 where solid != 0), computed on the device."""
+        out = np.empty((self.nxl, self.ny), dtype=self.np_dtype)
+        m = None if solid is None else np.ascontiguousarray(np.asarray(solid) != 0, dtype=np.uint8)
+        C.check(self._L.lbm_get_speed(self._h, None if m is None else self._p(m), self._p(out)))
+        return out
+
     def probe_line(self, axis, index, row=0):
         """(rho, ux, uy) along column x=index (axis 0) or row y=index (axis 1)."""
         n = self.ny if axis == 0 else self.nxl

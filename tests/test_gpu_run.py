@@ -148,3 +148,28 @@ def test_graph_replay_equals_plain_launches():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         assert np.array_equal(a[2][0], b[2][0]) and np.array_equal(a[2][1], b[2][1])
     assert np.max(np.abs(res[0][-1][1])) > 1e-6
+
+
+def test_speed_field_on_device_matches_plot_norm():
+    """lbm_get_speed == what plot_norm (plot.py:12-15) computes from lattice.u and lattice.lattice."""
+    import os
+    from lbm_b200.solver import Solver
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "run_turek30.npz"))
+    nx, ny = 160, 30
+    for dtype in ("f64", "f32"):
+        s = Solver(nx, ny, tau=0.62, right_wall="pressure", dtype=dtype)
+        s.set_links([cases.Obstacle(z["boundary"], z["ibb"])])
+        s.init_equilibrium(1.0, 0.03, 0.002)
+        row = s.wall_row(rho_right=np.ones(ny))
+        s.set_walls(row[None, :])
+        s.step(1)
+        s.step(25, 0, 0, macro_last=True)
+        rho, u = s.macro()
+        solid = np.zeros((nx, ny), dtype=np.uint8)
+        solid[40:50, 10:20] = 1
+        v = s.speed(solid)
+        ref = np.sqrt(u[0] ** 2 + u[1] ** 2)
+        ref[solid != 0] = -1.0
+        assert v.dtype == ref.dtype and np.array_equal(v, ref)
+        assert np.array_equal(s.speed(), np.sqrt(u[0] ** 2 + u[1] ** 2))
+        s.close()
