@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "d2q9.cuh"
 
 namespace lbm {
@@ -550,8 +552,7 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     const bool edge_row = y == 0 || y == p.ny - 1;
     const bool store_row = t >= PAD && t < PAD + TO;
     const T *const in_base = (stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0;
-    const int mask = stage == 0 ? R0 - 1 : R - 1, stride = stage == 0 ? COL0 : COL;
-    const RingSource<T, ROWS> src{in_base, mask, stride, ys};
+    const RingSource<T, ROWS> src{in_base, stage == 0 ? R0 - 1 : R - 1, stage == 0 ? COL0 : COL, ys};
     const T *const in_t = in_base + t;
     T *const out = lvl + stage * R * COL + M0 + t;           // own ring (stages 0 .. D-2)
     const T *const walls = p.wrow[stage];
@@ -561,54 +562,65 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     const int f_lo = inner_row ? max(lo, p.x_wl + 2) : 0x7fffffff;
     const int f_n = inner_row ? max(min(hi, p.x_wr >= 0 ? p.x_wr : 0x7fffffff) - f_lo, 0) : 0;
 
-    auto store = [&](int xc, const T (&G)[9]) {
-        if (stage == D - 1) {
-            if (store_row) {
-                const int idx = xc * p.pitch + y;
+    // The sweep, specialised by the role of the stage so that the ring geometry is a compile-time
+    // constant and the first stage's mbarrier waits / the last stage's global stores are not in the
+    // instruction stream of the others: FIRST reads the TMA ring, LAST stores to global memory.
+    auto sweep = [&](auto first_c, auto last_c) {
+        constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
+        constexpr int MASK = FIRST ? R0 - 1 : R - 1, STRIDE = FIRST ? COL0 : COL;
+        auto store = [&](int xc, const T (&G)[9]) {
+            if (LAST) {
+                if (store_row) {
+                    const int idx = xc * p.pitch + y;
 #pragma unroll
-                for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+                    for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+                }
+            } else {
+                T *o = out + (xc & (R - 1)) * COL;
+#pragma unroll
+                for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
             }
-        } else {
-            T *o = out + (xc & (R - 1)) * COL;
+        };
+        int x = xs0 - LAG * stage;
+        for (int s = 0; s < nsteps; s++, x++) {
+            if (FIRST) {
+                if (s == 0)
+                    for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
+                const int c = x + 1;
+                if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
+            }
+            if ((unsigned)(x - f_lo) < (unsigned)f_n) {
+                // bulk cell: pull, collide, store -- nothing else
+                const T *c0 = in_t + (x & MASK) * STRIDE;
+                const T *cm = in_t + ((x - 1) & MASK) * STRIDE;
+                const T *cp = in_t + ((x + 1) & MASK) * STRIDE;
+                T G[9], r, ux, uy;
 #pragma unroll
-            for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
+                for (int q = 0; q < 9; q++) {
+                    const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
+                    G[q] = c[q * ROWS - cy_of(q)];
+                }
+                collide_cell<A, T>(G, cf, false, r, ux, uy);
+                store(x, G);
+            } else if (row_ok && x >= lo && x < hi) {
+                // wall cells.  Left corners wait for the next column (see above); then two cells in one step
+                int n = 1, xc = x;
+                if (edge_row && x == p.x_wl) n = 0;
+                if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
+                for (; n > 0; n--, xc--) {
+                    T G[9];
+                    wall_cell<A, T>(p, walls, src, xc, y, G);
+                    store(xc, G);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
     };
-
-    int x = xs0 - LAG * stage;
-    for (int s = 0; s < nsteps; s++, x++) {
-        if (stage == 0) {
-            if (s == 0)
-                for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
-            const int c = x + 1;
-            if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
-        }
-        if ((unsigned)(x - f_lo) < (unsigned)f_n) {
-            // bulk cell: pull, collide, store -- nothing else
-            const T *c0 = in_t + (x & mask) * stride;
-            const T *cm = in_t + ((x - 1) & mask) * stride;
-            const T *cp = in_t + ((x + 1) & mask) * stride;
-            T G[9], r, ux, uy;
-#pragma unroll
-            for (int q = 0; q < 9; q++) {
-                const T *c = cx_of(q) > 0 ? cm : (cx_of(q) < 0 ? cp : c0);
-                G[q] = c[q * ROWS - cy_of(q)];
-            }
-            collide_cell<A, T>(G, cf, false, r, ux, uy);
-            store(x, G);
-        } else if (row_ok && x >= lo && x < hi) {
-            // wall cells.  Left corners wait for the next column (see above); then two cells in one step
-            int n = 1, xc = x;
-            if (edge_row && x == p.x_wl) n = 0;
-            if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
-            for (; n > 0; n--, xc--) {
-                T G[9];
-                wall_cell<A, T>(p, walls, src, xc, y, G);
-                store(xc, G);
-            }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-    }
+    using Yes = std::integral_constant<bool, true>;
+    using No = std::integral_constant<bool, false>;
+    if (stage == 0) sweep(Yes{}, No{});                      // D >= 2: the first stage is never the last
+    else if (stage == D - 1) sweep(No{}, Yes{});
+    else sweep(No{}, No{});
 }
 
 template <typename T, bool STRICT>
