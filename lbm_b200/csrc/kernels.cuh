@@ -581,8 +581,9 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                 for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
             }
         };
-        int x = xs0 - LAG * stage;
-        for (int s = 0; s < nsteps; s++, x++) {
+        // one sweep step on column x: cm / c0 / cp = this thread's row in the ring slots of columns x-1 / x / x+1,
+        // o = its row in the output slot of column x (unused by the last stage)
+        auto step = [&](int s, int x, const T *cm, const T *c0, const T *cp, T *o) {
             if (FIRST) {
                 if (s == 0)
                     for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
@@ -591,9 +592,6 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
             }
             if ((unsigned)(x - f_lo) < (unsigned)f_n) {
                 // bulk cell: pull, collide, store -- nothing else
-                const T *c0 = in_t + (x & MASK) * STRIDE;
-                const T *cm = in_t + ((x - 1) & MASK) * STRIDE;
-                const T *cp = in_t + ((x + 1) & MASK) * STRIDE;
                 T G[9], r, ux, uy;
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
@@ -601,7 +599,12 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                     G[q] = c[q * ROWS - cy_of(q)];
                 }
                 collide_cell<A, T>(G, cf, false, r, ux, uy);
-                store(x, G);
+                if (LAST) {
+                    store(x, G);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
+                }
             } else if (row_ok && x >= lo && x < hi) {
                 // wall cells.  Left corners wait for the next column (see above); then two cells in one step
                 int n = 1, xc = x;
@@ -614,7 +617,26 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        };
+        int x = xs0 - LAG * stage, s = 0;
+        if (!FIRST) {
+            // the 4-slot rings repeat every four columns: four steps per loop iteration with the slot
+            // addresses kept in registers (no address arithmetic in the bulk path)
+            const T *ib[R];
+            T *ob[R];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                ib[j] = in_t + ((x + j) & (R - 1)) * COL;
+                ob[j] = out + ((x + j) & (R - 1)) * COL;
+            }
+            for (; s + R <= nsteps; s += R, x += R) {
+#pragma unroll
+                for (int j = 0; j < R; j++) step(s + j, x + j, ib[(j + R - 1) & (R - 1)], ib[j], ib[(j + 1) & (R - 1)], ob[j]);
+            }
         }
+        for (; s < nsteps; s++, x++)
+            step(s, x, in_t + ((x - 1) & MASK) * STRIDE, in_t + (x & MASK) * STRIDE, in_t + ((x + 1) & MASK) * STRIDE,
+                 out + (x & (R - 1)) * COL);
     };
     using Yes = std::integral_constant<bool, true>;
     using No = std::integral_constant<bool, false>;
