@@ -6,6 +6,10 @@
 //                 first update on its tile plus a one-cell rim into shared memory and the second
 //                 update from shared memory, so the populations cross HBM once per two updates.
 //                 Same per-cell device functions, hence bit-identical to two step_kernel launches.
+//   stepw_kernel  up to FOUR updates per launch (wavefront temporal blocking): a block sweeps a strip
+//                 of rows along x, the updates form a pipeline of thread groups through rings of
+//                 columns in shared memory, the source streams in through TMA tensor copies issued
+//                 by a producer warp.  Bit-identical again; the default on obstacle-free lattices.
 //
 // Indexing: every population plane is addressed as  base_q[idx]  with a 32-bit cell index
 // idx = x*pitch + y and per-plane base pointers that live in the kernel parameters (constant

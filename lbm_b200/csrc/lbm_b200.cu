@@ -1,6 +1,7 @@
 // lbm_b200.cu -- sm_100a kernels and the C ABI (include/lbm_b200.h) of the D2Q9 time step.
 //
-// One fused kernel per lattice update: pull-stream from the post-collision array F of the
+// One fused kernel per lattice update -- or per two / three / four updates on obstacle-free
+// lattices (temporal blocking, kernels.cuh): pull-stream from the post-collision array F of the
 // previous update, obstacle (interpolated) bounce-back, Zou-He walls/corners, macro,
 // equilibrium, TRT collision, store.  See DESIGN.md for layout and roofline.
 #include <cuda.h>

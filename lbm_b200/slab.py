@@ -1,17 +1,19 @@
 """x-slab decomposition of the lattice over the GPUs of one box, one process per GPU.
 
 The reference has no distributed path; the analogue of its single address
-space is a domain split along x: rank r owns global columns [x0, x0+nxl) and keeps one halo
-column on each side.  Because y is the contiguous axis (lattice.py:155), a halo is one contiguous
-line per population.  After every update each interface exchanges the three populations that
-cross it:
+space is a domain split along x: rank r owns global columns [x0, x0+nxl) and keeps halo columns
+on each side (layout.halo = 4, the deepest multi-update launch).  Because y is the contiguous axis
+(lattice.py:155), a halo is one contiguous line per population.  After a single update each
+interface exchanges the three populations that cross it:
 
     to the right neighbour : q in {1, 5, 8} (c_x = +1) of the last owned column  -> its halo x = -1
     to the left  neighbour : q in {2, 6, 7} (c_x = -1) of the first owned column -> its halo x = nxl
 
-The update itself is the same kernel with the same per-cell arithmetic, so a slab run is bitwise
-identical to a single-GPU run.  Edge columns are updated first, their exchange (NCCL send/recv on a
-side stream) overlaps the interior update.
+Multi-update launches need deeper halos (see _plan and exchange_packed), obstacles two whole
+columns.  The update itself is the same kernel with the same per-cell arithmetic, so a slab run
+is bitwise identical to a single-GPU run.  For single- and two-update launches the edge columns
+are updated first and their exchange (NCCL send/recv on a high-priority side stream) overlaps the
+interior update; a wavefront launch covers the slab in one go and the exchange follows it.
 """
 import numpy as np
 
