@@ -124,6 +124,18 @@ def exchange_packed(view, nxl, rank, world, dist, halo, d, stage):
         view[:, h - d:h].copy_(stage["recv_l"])
 
 
+def launch_plan(n, depth):
+    """How n updates are grouped into launches of at most `depth` updates: [(updates of the launch,
+    updates of the launch after it)], the second entry being what the halo exchange that follows the
+    launch has to prepare (the last launch prepares for a full-depth one: what comes next is unknown)."""
+    plan, k = [], 0
+    while k < n:
+        d = min(depth, n - k)
+        plan.append((d, min(depth, n - k - d) or depth))
+        k += d
+    return plan
+
+
 class SlabSolver:
     """One rank's share of a slab-decomposed run (CUDA + NCCL)."""
 
@@ -285,17 +297,12 @@ class SlabSolver:
     def advance(self, first_row, n, depth, row_stride=1):
         """n lattice updates starting with wall row first_row, at most `depth` per launch."""
         k = 0
-        while k < n:
-            d = min(depth, n - k)
-            nxt = min(depth, n - k - d) or depth          # what the following launch will be
+        for d, nxt in launch_plan(n, depth):
             rows = [first_row + (k + j) * row_stride for j in range(d)]
-            if d >= 3:
+            if d >= 3 or (d == 2 and depth > 2):
                 self.updaten(rows, next_depth=nxt)
             elif d == 2:
-                if depth > 2:
-                    self.updaten(rows, next_depth=nxt)
-                else:
-                    self.update2(rows[0], rows[1], next_depth=nxt)
+                self.update2(rows[0], rows[1], next_depth=nxt)
             else:
                 self.update(rows[0], next_depth=nxt)
             k += d

@@ -125,3 +125,18 @@ def test_halo_exchange_feeds_the_pull_stream(world, nx):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, nx, 9, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)) and len(out) == world
+
+
+def test_launch_plan_groups_updates_and_announces_the_next_halo_depth():
+    assert slab.launch_plan(10, 4) == [(4, 4), (4, 2), (2, 4)]
+    assert slab.launch_plan(9, 4) == [(4, 4), (4, 1), (1, 4)]
+    assert slab.launch_plan(7, 3) == [(3, 3), (3, 1), (1, 3)]
+    assert slab.launch_plan(5, 2) == [(2, 2), (2, 1), (1, 2)]
+    assert slab.launch_plan(3, 1) == [(1, 1), (1, 1), (1, 1)]
+    assert slab.launch_plan(0, 4) == []
+    for n in range(1, 40):
+        for depth in (1, 2, 3, 4):
+            plan = slab.launch_plan(n, depth)
+            assert sum(d for d, _ in plan) == n and all(1 <= d <= depth for d, _ in plan)
+            for (d, nxt), (d2, _) in zip(plan[:-1], plan[1:]):
+                assert nxt == d2                     # every exchange prepares exactly the launch that follows
