@@ -169,7 +169,7 @@ int lbm_set_temporal_depth(lbm_t *h, int32_t depth);
 /* Launch-shape knobs (measurement, tests): "wave_chunk" = columns swept by one block of a
  * wavefront launch (default: by slab size), "wave_rows" = strip height (64 | 128), "pf_ahead" = L2
  * prefetch distance of step2_kernel in blocks, "graph" = 0 disables the CUDA-graph replay of
- * lbm_step batches on small lattices (>= 16 updates, <= 2^22 cells, non-default stream). */
+ * lbm_step batches on small lattices (>= 16 updates, <= 2^19 cells, non-default stream). */
 int lbm_set_tuning(lbm_t *h, const char *key, int64_t value);
 
 /* Stream + (I)BB + Zou-He of the current F with wall row `row`, no collision: materialises the

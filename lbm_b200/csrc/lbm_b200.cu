@@ -914,8 +914,10 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     // Small lattices are launch bound (4 us per update at 200 x 200, profiles/README.md): a batch of
     // updates is captured once into a CUDA graph and replayed (the wall table, force slots and
     // population buffers keep their addresses; their contents are read when the graph runs).
+    // (<= 2^19 cells: below the size at which multi-update kernels take over, so that a captured batch
+    // consists of step_kernel launches only)
     const bool graph_ok = h->use_graph && h->stream != nullptr && h->kind == kHaveF && n_updates >= 16 &&
-                          h->cfg.nxl * h->cfg.ny <= (1LL << 22);
+                          h->cfg.nxl * h->cfg.ny <= (1LL << 19);
     if (graph_ok) {
         lbm_handle::StepGraph *g = nullptr;
         for (auto &e : h->graphs)
