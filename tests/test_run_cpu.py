@@ -1,0 +1,181 @@
+"""CPU: the batched driver loop (lbm_b200/run.py) -- batching, replay of the per-iteration callbacks,
+the exact stop-rule rollback -- driven by a lattice that has the lazy / batched surface of
+lbm_b200.lattice.lattice but executes the oracle's phases on the host.  The result must equal the
+reference's plain loop (oracle.run_loop) bit for bit: same iteration count, same drag/lift series,
+same final arrays.  (On the GPU the same driver is covered by tests/test_gpu_run.py.)"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from lbm_b200 import cases
+from lbm_b200.run import run
+from oracle import oracle as orc
+
+_BC = ("zou_he_left_wall_velocity", "zou_he_right_wall_velocity", "zou_he_right_wall_pressure",
+       "zou_he_top_wall_velocity", "zou_he_bottom_wall_velocity", "zou_he_bottom_left_corner",
+       "zou_he_top_left_corner", "zou_he_top_right_corner", "zou_he_bottom_right_corner")
+
+
+class LazyOracleLattice(orc.OracleLattice):
+    """Oracle phases behind the deferred-execution interface of the GPU lattice: boundary calls are
+    recorded (with the wall arrays of that moment), the work of an iteration is executed by the next
+    macro() or by batch_updates()."""
+
+    def __init__(self, app):
+        super().__init__(app)
+        self._state = "fresh"            # fresh | macro_done | streamed
+        self._recorded = []              # [(method name, obstacle or None)] of the open BC window
+        self._row = np.zeros(5 * self.ny + 4 * self.nx)
+        self._replay = None
+        self._advanced = False           # collide + stream + BCs of the current iteration already executed
+        self._link_obstacles = []
+        self.batches = []
+
+    # -- wall rows ------------------------------------------------------------------------
+    def snapshot_walls(self):
+        nx, ny = self.nx, self.ny
+        return np.concatenate([self.u_left.reshape(-1), self.u_right.reshape(-1), self.u_top.reshape(-1),
+                               self.u_bot.reshape(-1), self.rho_right])
+
+    def _load_row(self, row):
+        nx, ny = self.nx, self.ny
+        self.u_left[:] = row[0:2 * ny].reshape(2, ny)
+        self.u_right[:] = row[2 * ny:4 * ny].reshape(2, ny)
+        self.u_top[:] = row[4 * ny:4 * ny + 2 * nx].reshape(2, nx)
+        self.u_bot[:] = row[4 * ny + 2 * nx:4 * ny + 4 * nx].reshape(2, nx)
+        self.rho_right[:] = row[4 * ny + 4 * nx:]
+
+    # -- execution ------------------------------------------------------------------------
+    def _advance(self):
+        """collide + stream of the current iteration, then its recorded boundary conditions with the
+        recorded wall row; returns the momentum-exchange sums per obstacle."""
+        now = self.snapshot_walls()
+        self._load_row(self._row)
+        orc.OracleLattice.equilibrium(self)
+        orc.OracleLattice.collision_stream(self)
+        obstacles = []
+        for name, obs in self._recorded:
+            if name == "bounce_back_obstacle":
+                orc.OracleLattice.bounce_back_obstacle(self, obs)
+                obstacles.append(obs)
+            else:
+                getattr(orc.OracleLattice, name)(self)
+        self._link_obstacles = obstacles
+        f = np.zeros((max(len(obstacles), 1), 2))
+        for k, obs in enumerate(obstacles):
+            cx, cy = orc.OracleLattice.drag_lift(self, obs, 1.0, 1.0, 1.0)      # C = -2 f
+            f[k] = (-0.5 * cx, -0.5 * cy)
+        self._load_row(now)
+        return f
+
+    def macro(self):
+        if self._state == "macro_done":
+            return
+        if self._state == "streamed" and not self._advanced:
+            self._advance()
+        orc.OracleLattice.macro(self)
+        self._state, self._advanced = "macro_done", False
+
+    def equilibrium(self):
+        if self._state == "fresh":
+            orc.OracleLattice.equilibrium(self)
+
+    def collision_stream(self):
+        assert self._state == "macro_done"
+        self._state, self._recorded = "streamed", []
+
+    def _record(self, name, obs=None):
+        assert self._state == "streamed" and not self._advanced
+        self._recorded.append((name, obs))
+        self._row = self.snapshot_walls()
+
+    def bounce_back_obstacle(self, obstacle):
+        self._record("bounce_back_obstacle", obstacle)
+
+    def drag_lift(self, obs, R_ref, U_ref, L_ref):
+        if self._replay is not None:
+            k = [i for i, o in enumerate(self._link_obstacles) if o is obs][0]
+            fx, fy = float(self._replay[k, 0]), float(self._replay[k, 1])
+        else:
+            assert self._state == "streamed"
+            if not self._advanced:
+                self._last_f = self._advance()
+                self._advanced = True
+            k = [i for i, o in enumerate(self._link_obstacles) if o is obs][0]
+            fx, fy = self._last_f[k]
+        return (-2.0 * fx / (R_ref * L_ref * U_ref ** 2), -2.0 * fy / (R_ref * L_ref * U_ref ** 2))
+
+    def batch_updates(self, rows):
+        assert self._state == "streamed"
+        rows = np.asarray(rows).reshape(-1, self._row.size)
+        self.batches.append(len(rows))
+        forces = []
+        for k, row in enumerate(rows):
+            self._row = row.copy()
+            if self._advanced:                       # (drag_lift already executed this iteration's tail)
+                f, self._advanced = self._last_f, False
+            else:
+                f = self._advance()
+            forces.append(f)
+            orc.OracleLattice.macro(self)
+            self._state = "macro_done"
+            if k + 1 < len(rows):
+                self._state = "streamed"             # same BC set for the following update
+        return np.array(forces)
+
+    def save_state(self):
+        self._saved = tuple(a.copy() for a in (self.g, self.g_up, self.rho, self.u)) + (self._advanced,)
+
+    def restore_state(self):
+        self.rollbacks = getattr(self, "rollbacks", 0) + 1
+        for a, b in zip((self.g, self.g_up, self.rho, self.u), self._saved[:4]):
+            a[:] = b
+        self._advanced = self._saved[4]
+
+
+for _name in _BC:
+    setattr(LazyOracleLattice, _name, (lambda n: lambda self: self._record(n))(_name))
+
+
+def _cases():
+    z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+
+    def turek(stop):
+        c = cases.Turek(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])], stop=stop)
+        if stop == "obs":
+            c.obs_cv_ct, c.obs_cv_nb = 5.0e-2, 40          # converges after a few hundred iterations
+        else:
+            c.it_max = 230
+        return c
+    return {"cavity": lambda: _with(cases.Cavity(L_lbm=24, sigma=20), it_max=157),
+            "turek_it": lambda: turek("it"), "turek_obs": lambda: turek("obs")}
+
+
+def _with(c, **kw):
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.mark.parametrize("name", ["cavity", "turek_it", "turek_obs"])
+@pytest.mark.parametrize("batch", [1, 7, 64])
+def test_batched_driver_equals_the_plain_loop(name, batch):
+    mk = _cases()[name]
+    ca, cb = mk(), mk()
+    la, lb = LazyOracleLattice(ca), orc.OracleLattice(cb)
+    na = run(la, ca, batch=batch, quiet=True)
+    nb = orc.run_loop(lb, cb)
+    assert na == nb and na > 50
+    if batch > 1:
+        assert max(la.batches) > 1                                   # really batched
+        if name == "turek_obs":
+            assert getattr(la, "rollbacks", 0) == 1                  # the stop rule fired inside a batch
+    if getattr(ca, "forces", None):
+        assert np.array_equal(np.array(ca.forces), np.array(cb.forces))
+    # the plain loop ends after set_bc of the last iteration; bring the lazy lattice to the same point
+    if la._state == "streamed" and not la._advanced:
+        la._advance()
+    for k in ("g", "g_up", "rho", "u"):
+        assert np.array_equal(getattr(la, k), getattr(lb, k)), k
