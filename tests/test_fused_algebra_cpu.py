@@ -59,3 +59,35 @@ def test_moment_form_equals_macro_equilibrium_trt(tau):
     assert np.max(np.abs(uy - lo.u[1])) < 5e-16 + 1e-15 * np.max(np.abs(lo.u))
     # conservation: the collision keeps mass and momentum of every cell
     assert np.max(np.abs(F.sum(axis=0) - G.sum(axis=0))) < 1e-14
+
+
+def test_deviation_storage_is_the_same_update():
+    """f32 state is stored as h_q = f_q - w_q (d2q9.cuh: Stored<float>): the fused collision on h, with
+    rho = 1 + sum(h) and om_p w dr in place of om_p w rho, yields F - w (checked in double precision)."""
+    rng = np.random.default_rng(3)
+    om_p, om_m = 1.0 / 0.56, 1.0 / (0.25 / 0.06 + 0.5)
+    G = W[:, None] * (1.0 + 0.03 * rng.standard_normal((9, 500)))
+    F, r, ux, uy = collide_fused_numpy(G, om_p, om_m)
+    H = G - W[:, None]
+    # collide_fused with dev = true, expression by expression
+    one_m_omp = 1.0 - om_p
+    a_self, a_opp = 1.0 - 0.5 * (om_p + om_m), 0.5 * (om_p - om_m)
+    wp, wq, wm = om_p * W, 4.5 * om_p * W, 3.0 * om_m * W
+    s = (((H[0] + H[1]) + (H[2] + H[3])) + ((H[4] + H[5]) + (H[6] + H[7]))) + H[8]
+    rho = 1.0 + s
+    d56, d78 = H[5] - H[6], H[7] - H[8]
+    mx, my = ((H[1] - H[2]) + d56) - d78, ((H[3] - H[4]) + d56) + d78
+    y = 1.0 / rho
+    ms = [mx, my, mx + my, my - mx]
+    h = 1.5 * (mx * mx + my * my)
+    Fh = np.empty_like(H)
+    Fh[0] = (one_m_omp * H[0] + s * wp[0]) - (h * wp[0]) * y
+    for k in range(4):
+        q, qb = 2 * k + 1, 2 * k + 2
+        K = wq[q] * (ms[k] * ms[k]) - h * wp[q]
+        M = wm[q] * ms[k]
+        rp = s * wp[q]
+        Fh[q] = K * y + (a_self * H[q] + ((rp + M) - a_opp * H[qb]))
+        Fh[qb] = K * y + (a_self * H[qb] + ((rp - M) - a_opp * H[q]))
+    assert np.max(np.abs(rho - r)) < 1e-15
+    assert np.max(np.abs((Fh + W[:, None]) - F)) < 1e-15     # a few ulps of the populations (0.03 .. 0.44)
