@@ -142,6 +142,20 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
  * copy is asynchronous: keep it unchanged until the next lbm_sync / lbm_get_*. */
 int64_t lbm_wall_row_len(const lbm_t *h);
 int lbm_set_walls(lbm_t *h, int64_t n_rows, const double *rows_host);
+/* The same table with ONE row given as the reference's five arrays (lattice.py:160-164: u_left[2][ny],
+ * u_right[2][ny], u_top[2][nx], u_bot[2][nx], rho_right[ny]; NULL = zeros): the BASE profiles of a
+ * ramped run, uploaded once. */
+int lbm_set_wall_profiles(lbm_t *h, const double *u_left, const double *u_right, const double *u_top,
+                          const double *u_bot, const double *rho_right);
+/* Inlet ramp.  Every reference app scales its wall velocity profile by one scalar per iteration,
+ * ret(it) = 1 - exp(-it^2 / (2 sigma^2))  (cavity.py:70-73, turek.py:99-104, poiseuille.py, array.py):
+ * with a ramp table set, the `row` arguments of lbm_step / lbm_step*_columns / lbm_apply_bc /
+ * lbm_probe_line are ITERATION indices it in [it0, it0+n): the update multiplies the velocity entries
+ * of profile row (it % n_rows) by ret_host[it - it0] (rho_right is not scaled, turek.py:109), so a
+ * step's host->device traffic is 8 bytes instead of a wall row.  The product is one rounded
+ * multiplication, as in the apps (u_lbm*ret; (ret*u_lbm)*profile).  n = 0 removes the table.  If
+ * ret_host is pinned the copy is asynchronous: keep it unchanged until the next lbm_sync / lbm_get_*. */
+int lbm_set_ramp(lbm_t *h, const double *ret_host, int64_t it0, int64_t n);
 
 /* n_updates fused updates; update s uses wall row first_row + s*row_stride and stores the
  * momentum-exchange sums of every obstacle in force slot s.  Replaces one pass of
@@ -167,7 +181,8 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
 int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int64_t *rows);
 int lbm_set_temporal_depth(lbm_t *h, int32_t depth);
 /* Launch-shape knobs (measurement, tests): "wave_chunk" = columns swept by one block of a
- * wavefront launch (default: by slab size), "wave_rows" = strip height (64 | 128), "pf_ahead" = L2
+ * wavefront launch (default: by slab size), "wave_tail" = width of the short chunks that end a
+ * wavefront launch (-1 auto, 0 uniform chunks), "wave_rows" = strip height (64 | 128), "pf_ahead" = L2
  * prefetch distance of step2_kernel in blocks, "graph" = 0 disables the CUDA-graph replay of
  * lbm_step batches on small lattices (>= 16 updates, <= 2^19 cells, non-default stream). */
 int lbm_set_tuning(lbm_t *h, const char *key, int64_t value);
@@ -200,6 +215,43 @@ int lbm_get_speed(lbm_t *h, const unsigned char *solid_host, void *speed_host);
  * (poiseuille.py:128-152) without a full-field transfer.  axis 0: column x = index (ny values),
  * axis 1: row y = index (nxl values).  out_host: [rho | ux | uy], 3*n elements of the handle dtype. */
 int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out_host);
+
+/* ---- x-slab runs, one process per GPU: halo exchange through peer memory (NVLink) --------------------
+ * The reference is one address space; its analogue over several GPUs is a split
+ * along x with kHalo = 4 halo columns per side.  Instead of sending halos after a launch, the multi-update
+ * kernel's last stage stores its edge columns straight into the neighbour's halo columns:
+ *   lbm_peer_export   describes this handle's population buffers and flag words (CUDA IPC handles; the
+ *                     buffers must be library-owned, i.e. no lbm_bind_state);
+ *   lbm_peer_attach   maps a neighbour's buffers (side 0 = left, x0 - 1; side 1 = right).  From then on
+ *                     every lbm_stepn_columns launch also fills that neighbour's halo, and every launch
+ *                     first waits (on the device) until both neighbours have signalled the previous group;
+ *   lbm_peer_push     copies the kHalo edge columns of the current (which = 0) or other (1) buffer into the
+ *                     neighbours' halos of the same buffer -- for launches that do not do it themselves
+ *                     (lbm_step_columns, lbm_step2_columns, initial state);
+ *   lbm_peer_signal   call once after the launches (and pushes) of one update group, before lbm_flip: tells
+ *                     both neighbours (flag words in their memory, release/acquire at system scope) that
+ *                     their halos are complete and that this rank is done reading its source buffer.
+ * All ranks must issue the same sequence of update groups.  lbm_sync reports a wait that timed out
+ * (tuning key "peer_timeout_ms", default 20 s) instead of hanging the device. */
+#define LBM_IPC_HANDLE_BYTES 64
+typedef struct lbm_peer_info {
+    unsigned char mem[2][LBM_IPC_HANDLE_BYTES];  /* cudaIpcMemHandle_t of the two population buffers */
+    unsigned char flags[LBM_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the flag words */
+    uint64_t addr[2], flags_addr;                /* the same as addresses, for peers inside one process */
+    int64_t pid, device;
+    int64_t x0, nxl, origin, plane, pitch, elem_size;
+} lbm_peer_info;
+int lbm_peer_export(lbm_t *h, lbm_peer_info *out);
+int lbm_peer_attach(lbm_t *h, int32_t side, const lbm_peer_info *neighbour);
+int lbm_peer_detach(lbm_t *h);
+int lbm_peer_push(lbm_t *h, int32_t which);
+int lbm_peer_signal(lbm_t *h);
+
+/* Wrap-around 64-bit sum of the bit patterns of the current population array (owned cells, nine planes;
+ * f32: the 32-bit patterns, zero-extended): equal arrays give equal sums whatever the slab split, so the
+ * per-rank values of a slab run add up (mod 2^64) to the single-GPU value.  Parity aid for lattices that
+ * do not fit a host comparison (bench.py parity.state_bits_sum, tests at 32768^2). */
+int lbm_state_checksum(lbm_t *h, uint64_t *out);
 
 /* Launch counter: kernels launched by this handle since creation (bench.py gpu_launches). */
 int64_t lbm_launch_count(const lbm_t *h);

@@ -33,6 +33,14 @@ class LbmLayout(ctypes.Structure):
                 ("elem_size", c_i64), ("halo", c_i64)]
 
 
+class LbmPeerInfo(ctypes.Structure):
+    _fields_ = [("mem", (ctypes.c_ubyte * 64) * 2), ("flags", ctypes.c_ubyte * 64),
+                ("addr", ctypes.c_uint64 * 2), ("flags_addr", ctypes.c_uint64),
+                ("pid", c_i64), ("device", c_i64),
+                ("x0", c_i64), ("nxl", c_i64), ("origin", c_i64), ("plane", c_i64), ("pitch", c_i64),
+                ("elem_size", c_i64)]
+
+
 class LbmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("lbm_b200 error %d: %s" % (code, msg))
@@ -58,6 +66,8 @@ SIGNATURES = {
     "lbm_set_links": (ctypes.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32]),
     "lbm_wall_row_len": (c_i64, [c_vp]),
     "lbm_set_walls": (ctypes.c_int, [c_vp, c_i64, c_vp]),
+    "lbm_set_wall_profiles": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "lbm_set_ramp": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64]),
     "lbm_step": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, ctypes.c_uint32]),
     "lbm_step_columns": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_uint32]),
     "lbm_flip": (ctypes.c_int, [c_vp]),
@@ -71,8 +81,14 @@ SIGNATURES = {
     "lbm_forces_now": (ctypes.c_int, [c_vp, c_vp]),
     "lbm_get_populations": (ctypes.c_int, [c_vp, c_i32, c_vp]),
     "lbm_get_macro": (ctypes.c_int, [c_vp, c_vp, c_vp]),
-"lbm_get_speed": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "lbm_get_speed": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "lbm_probe_line": (ctypes.c_int, [c_vp, c_i32, c_i64, c_i64, c_vp]),
+    "lbm_peer_export": (ctypes.c_int, [c_vp, ctypes.POINTER(LbmPeerInfo)]),
+    "lbm_peer_attach": (ctypes.c_int, [c_vp, c_i32, ctypes.POINTER(LbmPeerInfo)]),
+    "lbm_peer_detach": (ctypes.c_int, [c_vp]),
+    "lbm_peer_push": (ctypes.c_int, [c_vp, c_i32]),
+    "lbm_peer_signal": (ctypes.c_int, [c_vp]),
+    "lbm_state_checksum": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "lbm_launch_count": (c_i64, [c_vp]),
     "lbm_last_step_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
 }

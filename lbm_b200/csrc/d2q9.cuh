@@ -110,8 +110,9 @@ __host__ __device__ constexpr double weight_of(int q) { return q == 0 ? 4.0 / 9.
 template <typename T> struct Coef {
     T one_m_omp, om_p;        // q = 0:      (1-om_p) g0 + om_p geq0                 nb.py:26
     T a_self, a_opp, a_eq;    // q >= 1:     1-(om_p+om_m)/2, (om_p-om_m)/2, (om_p+om_m)/2   nb.py:31-35
-    // FUSED arithmetic (collide_fused): w_q om_p for the three weight classes, 4.5 w_q om_p, 3 w_q om_m
-    T wp0, wp1, wp5, wq1, wq5, wm1, wm5;
+    // FUSED arithmetic (collide_fused): w_q om_p for the three weight classes, 1.5 w_q om_p, 4.5 w_q om_p,
+    // 3 w_q om_m, and the pair coefficients (1 - om_p)/2, (1 - om_m)/2
+    T wp0, wp1, wp5, wh0, wh1, wh5, wq1, wq5, wm1, wm5, cs, cd;
 };
 
 // rho = sum_q g_q in index order; u = (c . g) / rho     (lattice.py:181-189, oracle orc_macro)
@@ -145,45 +146,47 @@ __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr
 // coefficients a_self - a_opp + a_eq + a_opp = 1 and w_q = w_qbar, so it maps h to h unchanged.
 //
 // FUSED arithmetic (collide_fused): lattice.macro + nb_equilibrium + the TRT collision in one
-// expression tree, written in the MOMENTS  rho, m = rho u  and the symmetric / antisymmetric parts of
-// the equilibrium.  With  eq_s = (geq_q + geq_qbar)/2 = w rho (1 + 4.5 s^2 - v),  eq_a = (geq_q -
-// geq_qbar)/2 = 3 w rho s  (s = c_q.u, v = 1.5 u.u)  and  a_eq + a_opp = om_p,  a_eq - a_opp = om_m
-// the TRT update of a pair is
-//     F_q    = a_self g_q    - a_opp g_qbar + om_p eq_s + om_m eq_a
-//     F_qbar = a_self g_qbar - a_opp g_q    + om_p eq_s - om_m eq_a
+// expression tree, written in the MOMENTS  rho, m = rho u  and, per opposite pair (q, qbar), in the
+// pair's SUM and DIFFERENCE.  With  eq_s = (geq_q + geq_qbar)/2 = w rho (1 + 4.5 s^2 - v),  eq_a = (geq_q -
+// geq_qbar)/2 = 3 w rho s  (s = c_q.u, v = 1.5 u.u)  and  a_eq + a_opp = om_p,  a_eq - a_opp = om_m,
+// a_self - a_opp = 1 - om_p,  a_self + a_opp = 1 - om_m  the TRT update (nb.py:31-35) of a pair is
+//     (F_q + F_qbar)/2 = (1 - om_p)/2 (g_q + g_qbar) + om_p eq_s        =: Fs
+//     (F_q - F_qbar)/2 = (1 - om_m)/2 (g_q - g_qbar) + om_m eq_a        =: Fd
+//     F_q = Fs + Fd,   F_qbar = Fs - Fd
 // and, with  m_s = c_q.m = rho s  and  y = 1/rho,
 //     om_p eq_s = om_p w rho + y (4.5 om_p w m_s^2 - 1.5 om_p w m.m),      om_m eq_a = 3 om_m w m_s .
-// Everything except the last multiply-add by y is independent of the reciprocal: the dependent chain
-// of a cell is  9 loads -> 4 additions -> seed + 3 FMAs -> 1 FMA  (the multi-update kernels are bound
-// by FP64 dependent-issue latency, profiles/README.md), 74 FP64 instructions in all.  Algebraically
-// identical to lattice.py:181-189 + nb.py:10-17 + 25-35; rounding differs at the 1e-16 level like any
-// FMA contraction does.  Deviation storage (f32): om_p (eq_s - w) = om_p w dr + y (...), same form.
+// The pair sums and differences are the ones the moments are built from anyway (rho = g_0 + sum of the
+// four pair sums, m from the four pair differences), so the whole cell costs 63 FP64 instructions
+// (the plain pair form  a_self g_q - a_opp g_qbar + ...  of round 1 took 76), and everything except the
+// last multiply-add by y is independent of the reciprocal: the dependent chain of a cell is
+// 9 loads -> 4 additions -> seed + 3 FMAs -> 1 FMA -> 1 addition  (the multi-update kernels are bound by
+// FP64 issue and dependent-issue latency, profiles/README.md).  Algebraically identical to
+// lattice.py:181-189 + nb.py:10-17 + 25-35; rounding differs at the 1e-16 level like any FMA
+// contraction does.  Deviation storage (f32): om_p (eq_s - w) = om_p w dr + y (...), same form.
 template <typename A, typename T>
 __device__ __forceinline__ void collide_fused(T (&G)[9], const Coef<T> &c, bool want_u, T &r, T &ux, T &uy)
 {
     constexpr bool dev = Stored<T>::dev;
-    const T sum = (((G[0] + G[1]) + (G[2] + G[3])) + ((G[4] + G[5]) + (G[6] + G[7]))) + G[8];
+    const T S[4] = {G[1] + G[2], G[3] + G[4], G[5] + G[6], G[7] + G[8]};
+    const T D[4] = {G[1] - G[2], G[3] - G[4], G[5] - G[6], G[7] - G[8]};
+    const T sum = G[0] + ((S[0] + S[1]) + (S[2] + S[3]));
     r = dev ? T(1.0) + sum : sum;
-    const T d56 = G[5] - G[6], d78 = G[7] - G[8];
-    const T mx = ((G[1] - G[2]) + d56) - d78;
-    const T my = ((G[3] - G[4]) + d56) + d78;
+    const T mx = (D[0] + D[2]) - D[3];
+    const T my = (D[1] + D[2]) + D[3];
     const T y = A::rcp(r);
     const T ms[4] = {mx, my, mx + my, my - mx};
-    const T h = T(1.5) * (mx * mx + my * my);
+    const T m2 = mx * mx + my * my;
     const T rp0 = sum * c.wp0, rp1 = sum * c.wp1, rp5 = sum * c.wp5;    // om_p w rho  (f32: om_p w dr)
-    const T hp0 = h * c.wp0, hp1 = h * c.wp1, hp5 = h * c.wp5;          // 1.5 om_p w m.m
+    const T hp0 = m2 * c.wh0, hp1 = m2 * c.wh1, hp5 = m2 * c.wh5;       // 1.5 om_p w m.m
     G[0] = (c.one_m_omp * G[0] + rp0) - hp0 * y;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int q = 2 * k + 1, qb = q + 1;
         const T K = (k < 2 ? c.wq1 : c.wq5) * (ms[k] * ms[k]) - (k < 2 ? hp1 : hp5);
-        const T M = (k < 2 ? c.wm1 : c.wm5) * ms[k];
-        const T rp = k < 2 ? rp1 : rp5;
-        const T gq = G[q], gb = G[qb];
-        const T bq = c.a_self * gq + ((rp + M) - c.a_opp * gb);
-        const T bb = c.a_self * gb + ((rp - M) - c.a_opp * gq);
-        G[q] = K * y + bq;
-        G[qb] = K * y + bb;
+        const T Fs = K * y + (c.cs * S[k] + (k < 2 ? rp1 : rp5));
+        const T Fd = c.cd * D[k] + (k < 2 ? c.wm1 : c.wm5) * ms[k];
+        G[q] = Fs + Fd;
+        G[qb] = Fs - Fd;
     }
     if (want_u) {   // lattice.macro's u, only where it is stored
         ux = mx * y;

@@ -48,6 +48,20 @@ template <typename T> struct StepParams {
     int pf_ahead;           // step2_kernel: L2 prefetch distance in blocks (0 = off)
     const T *wrow[4];       // stepw_kernel: wall rows of the (up to four) updates of one launch
     int chunk;              // stepw_kernel: columns swept by one block
+    // Ramp: the velocity entries of a wall row are multiplied by *scale (device scalar, 1 when no ramp
+    // table is set): the apps' inlet ramp  u_wall(it) = ret(it) * base profile  (cavity.py:70-73,
+    // turek.py:99-104) costs 8 bytes of host->device traffic per update instead of a whole row.
+    const T *scale;         // of `walls`
+    const T *scale2;        // of `walls2`
+    const T *wscale[4];     // of `wrow[k]`
+    // stepw_kernel, slab runs: the last stage stores its first / last kHalo columns also into the halo
+    // columns of the left / right neighbour's destination buffer (peer memory over NVLink).
+    // peer_X + q*peer_plane_X + xc*pitch + y  is the neighbour's copy of my cell (q, xc, y).
+    T *peer_l, *peer_r;
+    long long peer_plane_l, peer_plane_r;
+    // non-uniform chunks: blockIdx.y < n_main sweeps `chunk` columns, later blocks `chunk_tail` columns
+    // (short blocks at the end of the launch shorten its tail)
+    int n_main, chunk_tail;
 };
 
 struct LinkParams {
@@ -96,11 +110,12 @@ template <typename T, int SP, int NS> struct SharedSource {
 // Corner cells copy rho and u from the x-neighbour on the same horizontal wall
 // (nb.py:254-257 and siblings); its Zou-He density is recomputed here from the source.
 template <typename A, typename T, typename Src>
-__device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *walls, const Src &src,
+__device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *walls, const T *scale, const Src &src,
                                             int x, int y, T (&G)[9], T &r, T &ux, T &uy)
 {
     const bool L = x == p.x_wl, R = x == p.x_wr, B = y == 0, Tp = y == p.ny - 1;
     if (!(L | R | B | Tp)) return false;
+    const T sc = *scale;            // ramp factor of this update (1 without a ramp table: x * 1 is exact)
     const int gx = p.gx0 + x;
     const T *ul = walls, *ur = ul + 2 * p.ny, *ut = ur + 2 * p.ny, *ub = ut + 2 * p.gnx,
             *rr = ub + 2 * p.gnx;
@@ -108,25 +123,25 @@ __device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *wal
         const int xn = L ? x + 1 : x - 1;
         const int gxn = L ? gx + 1 : gx - 1;
         const T *uw = B ? ub : ut;
-        ux = uw[gxn];
-        uy = uw[p.gnx + gxn];
+        ux = A::mul(uw[gxn], sc);
+        uy = A::mul(uw[p.gnx + gxn], sc);
         T N[9], dr;
         src(xn, B ? 0 : p.ny - 1, N);
         r = B ? ZouHe<A, T>::bottom_rho(N[0], N[1], N[2], N[4], N[6], N[8], uy, dr)
               : ZouHe<A, T>::top_rho(N[0], N[1], N[2], N[3], N[5], N[7], uy, dr);
         ZouHe<A, T>::corner(G, L, B, r, dr, ux, uy);
     } else if (B) {
-        ux = ub[gx]; uy = ub[p.gnx + gx];
+        ux = A::mul(ub[gx], sc); uy = A::mul(ub[p.gnx + gx], sc);
         ZouHe<A, T>::bottom(G, ux, uy, r);
     } else if (Tp) {
-        ux = ut[gx]; uy = ut[p.gnx + gx];
+        ux = A::mul(ut[gx], sc); uy = A::mul(ut[p.gnx + gx], sc);
         ZouHe<A, T>::top(G, ux, uy, r);
     } else if (L) {
-        ux = ul[y]; uy = ul[p.ny + y];
+        ux = A::mul(ul[y], sc); uy = A::mul(ul[p.ny + y], sc);
         ZouHe<A, T>::left(G, ux, uy, r);
     } else {
-        ux = ur[y]; uy = ur[p.ny + y];
-        r = rr[y];  // only used by the pressure variant
+        ux = A::mul(ur[y], sc); uy = A::mul(ur[p.ny + y], sc);
+        r = rr[y];  // only used by the pressure variant; the outlet density is not ramped (turek.py:109)
         ZouHe<A, T>::right(G, ux, uy, r, p.right_pressure != 0);
     }
     return true;
@@ -140,7 +155,7 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
     const int idx = x * p.pitch + y;
     if (MODE != kCollideOnly) {
         T r, ux, uy;
-        const bool on_wall = apply_walls<A, T>(p, p.walls, GlobalSource<T>{p}, x, y, G, r, ux, uy);
+        const bool on_wall = apply_walls<A, T>(p, p.walls, p.scale, GlobalSource<T>{p}, x, y, G, r, ux, uy);
         if (MODE == kStreamOnly) {
             if (on_wall && p.rho_out) {
                 p.rho_out[idx] = r;
@@ -317,7 +332,7 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             T r, ux, uy;
-            apply_walls<A, T>(p, p.walls, gsrc, x[k], y[k], G[k], r, ux, uy);
+            apply_walls<A, T>(p, p.walls, p.scale, gsrc, x[k], y[k], G[k], r, ux, uy);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -372,7 +387,7 @@ step2_kernel(const __grid_constant__ StepParams<T> p)
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
             T r, ux, uy;
-            apply_walls<A, T>(p, p.walls2, ssrc, x[k], y[k], G[k], r, ux, uy);
+            apply_walls<A, T>(p, p.walls2, p.scale2, ssrc, x[k], y[k], G[k], r, ux, uy);
         }
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -493,11 +508,11 @@ template <typename T, int ROWS> struct RingSource {
 // sequence, kept out of line so that the bulk path of stepw_kernel stays a straight run of
 // loads, arithmetic and stores (the two would otherwise be merged back into one by the compiler).
 template <typename A, typename T, typename Src>
-__device__ __noinline__ void wall_cell(const StepParams<T> &p, const T *walls, const Src &src, int xc, int y, T *out)
+__device__ __noinline__ void wall_cell(const StepParams<T> &p, const T *walls, const T *scale, const Src &src, int xc, int y, T *out)
 {
     T G[9], r, ux, uy;
     src(xc, y, G);
-    apply_walls<A, T>(p, walls, src, xc, y, G, r, ux, uy);
+    apply_walls<A, T>(p, walls, scale, src, xc, y, G, r, ux, uy);
     collide_cell<A, T>(G, p.coef, false, r, ux, uy);
 #pragma unroll
     for (int q = 0; q < 9; q++) out[q] = G[q];
@@ -520,7 +535,9 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
 
     const int stage = threadIdx.x / TYB, t = threadIdx.x - stage * TYB;
     const int ys = (int)blockIdx.x * TO - PAD, y = ys + t;
-    const int ca = p.xa + (int)blockIdx.y * p.chunk, cb = min(ca + p.chunk, p.xb);   // output columns [ca, cb)
+    const int by = (int)blockIdx.y;                          // chunk: `chunk` columns, the last blocks of the launch `chunk_tail`
+    const int ca = by < p.n_main ? p.xa + by * p.chunk : p.xa + p.n_main * p.chunk + (by - p.n_main) * p.chunk_tail;
+    const int cb = min(ca + (by < p.n_main ? p.chunk : p.chunk_tail), p.xb);         // output columns [ca, cb)
     const int xs0 = ca - (D - 1);                            // first column of stage 0
     const int c_first = xs0 - 2, c_last = cb + D - 1;        // level-0 columns that are loaded
     const int nsteps = (cb - ca) + 2 * (D - 1) + LAG * (D - 1);
@@ -555,11 +572,14 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     const bool row_ok = y >= 0 && y < p.ny;
     const bool edge_row = y == 0 || y == p.ny - 1;
     const bool store_row = t >= PAD && t < PAD + TO;
+    // slab runs: this chunk's share of the kHalo edge columns also goes to the neighbour's halo (peer memory)
+    const bool push_l = p.peer_l != nullptr && ca < kHalo, push_r = p.peer_r != nullptr && cb > p.nxl - kHalo;
     const T *const in_base = (stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0;
     const RingSource<T, ROWS> src{in_base, stage == 0 ? R0 - 1 : R - 1, stage == 0 ? COL0 : COL, ys};
     const T *const in_t = in_base + t;
     T *const out = lvl + stage * R * COL + M0 + t;           // own ring (stages 0 .. D-2)
     const T *const walls = p.wrow[stage];
+    const T *const wscale = p.wscale[stage];
     const Coef<T> cf = p.coef;
     // columns whose cells see no wall and no deferred corner, for a row that is not a wall row: the bulk path
     const bool inner_row = y > 0 && y < p.ny - 1;
@@ -578,6 +598,14 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                     const int idx = xc * p.pitch + y;
 #pragma unroll
                     for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+                    if (push_l && xc < kHalo) {
+#pragma unroll
+                        for (int q = 0; q < 9; q++) p.peer_l[q * p.peer_plane_l + idx] = G[q];
+                    }
+                    if (push_r && xc >= p.nxl - kHalo) {
+#pragma unroll
+                        for (int q = 0; q < 9; q++) p.peer_r[q * p.peer_plane_r + idx] = G[q];
+                    }
                 }
             } else {
                 T *o = out + (xc & (R - 1)) * COL;
@@ -616,7 +644,7 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                 if (edge_row && x == p.x_wl + 1 && x - 1 >= lo) n = 2;
                 for (; n > 0; n--, xc--) {
                     T G[9];
-                    wall_cell<A, T>(p, walls, src, xc, y, G);
+                    wall_cell<A, T>(p, walls, wscale, src, xc, y, G);
                     store(xc, G);
                 }
             }
@@ -670,7 +698,7 @@ probe_kernel(const __grid_constant__ StepParams<T> p, int axis, int index, int n
     T G[9], r, ux, uy;
     const GlobalSource<T> gsrc{p};
     gsrc(x, y, G);
-    apply_walls<A, T>(p, p.walls, gsrc, x, y, G, r, ux, uy);
+    apply_walls<A, T>(p, p.walls, p.scale, gsrc, x, y, G, r, ux, uy);
     T dr;
     macro<A, T>(G, r, ux, uy, dr);
     out[k] = r;
@@ -693,6 +721,30 @@ speed_kernel(const T *ux, const T *uy, const unsigned char *solid, T *out, int p
     T v = sizeof(T) == 8 ? (T)__dsqrt_rn((double)v2) : (T)__fsqrt_rn((float)v2);
     if (solid && solid[c]) v = T(-1.0);
     out[c] = v;
+}
+
+// Wrap-around 64-bit sum of the bit patterns of the owned cells of one population buffer (all nine
+// planes): an order-independent fingerprint that is equal for equal arrays -- parity of runs too large
+// to compare on the host (32768^2) and of slab runs against single-GPU runs.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+checksum_kernel(const T *f, long long plane, int pitch, int nxl, int ny, unsigned long long *out)
+{
+    unsigned long long acc = 0;
+    const long long cells = (long long)nxl * ny;
+    for (long long c = (long long)blockIdx.x * kBlock + threadIdx.x; c < cells; c += (long long)gridDim.x * kBlock) {
+        const int x = (int)(c / ny), y = (int)(c - (long long)x * ny);
+        const long long idx = (long long)x * pitch + y;
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const T v = f[q * plane + idx];
+            if (sizeof(T) == 8) acc += (unsigned long long)__double_as_longlong((double)v);
+            else acc += (unsigned long long)(unsigned int)__float_as_int((float)v);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
 // uniform equilibrium fill (initial state of every reference app: g = w_q rho at u = 0)
@@ -723,6 +775,61 @@ equilibrium_kernel(T *dst, long long plane, int pitch, int nxl, int ny, const T 
     equilibrium<Ar<T, STRICT>, T>(E, rho[cell], u[cell], u[(long long)nxl * pitch + cell]);
 #pragma unroll
     for (int q = 0; q < 9; q++) dst[q * plane + cell] = E[q];
+}
+
+// ---------------------------------------------------------------------------------------
+// Slab runs, one process per GPU: halo exchange through peer memory (NVLink), no host in the loop.
+//
+//   peer_push_kernel    copies my first / last kHalo columns (all nine planes) into the neighbours' halo
+//                       columns -- used after launches that do not store there themselves
+//                       (step_kernel, step2_kernel; stepw_kernel's last stage does).
+//   peer_signal_kernel  after the launches of one update group: publishes the group's sequence number
+//                       in the neighbours' flag words (release at system scope).
+//   peer_wait_kernel    before the next launch: spins until both neighbours have published that
+//                       number (their stores into my halos are then visible, and they are done reading
+//                       the buffer my next launch will store into).  A time-out records an error word
+//                       instead of hanging the device.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+peer_push_kernel(const T *src, T *peer_l, T *peer_r, long long plane, long long peer_plane_l, long long peer_plane_r,
+                 int pitch, int nxl, int ny)
+{
+    const int y = blockIdx.x * kBlock + threadIdx.x;
+    if (y >= ny) return;
+    const int q = blockIdx.y / (2 * kHalo), k = blockIdx.y % (2 * kHalo);
+    const bool left = k < kHalo;
+    const int xc = left ? k : nxl - 2 * kHalo + k;           // my column: 0..kHalo-1 or nxl-kHalo..nxl-1
+    T *peer = left ? peer_l : peer_r;
+    if (!peer) return;
+    const long long idx = (long long)xc * pitch + y;
+    peer[q * (left ? peer_plane_l : peer_plane_r) + idx] = src[q * plane + idx];
+}
+
+__global__ void peer_signal_kernel(unsigned int *flag_l, unsigned int *flag_r, unsigned int seq)
+{
+    __threadfence_system();
+    if (flag_l) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_l), "r"(seq) : "memory");
+    if (flag_r) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_r), "r"(seq) : "memory");
+}
+
+__global__ void peer_wait_kernel(const unsigned int *flags, int need_l, int need_r, unsigned int seq,
+                                 unsigned int *err, unsigned long long timeout_ns)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? need_l : need_r)) continue;
+        for (;;) {
+            unsigned int v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + side) : "memory");
+            if ((int)(v - seq) >= 0) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) { *err = seq; return; }
+            __nanosleep(200);
+        }
+    }
 }
 
 }  // namespace lbm

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "../../include/lbm_b200.h"
 
 #include "kernels.cuh"
@@ -69,13 +71,28 @@ struct lbm_handle {
     int wave_occ[5] = {1, 1, 1, 1, 1};   // resident blocks per SM of stepw_kernel<.., D, ..>
     TensorMap tmap[2];            // one 3-D tensor map per population buffer (stepw_kernel's TMA loads)
     int tmap_rows = 0;            // strip geometry (rows, depth) the maps were built for (0 = not built)
-    int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks (+3.5 % measured at 16384^2 f64)
+    int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks: two blocks per SM (+3.5 % measured at
+                                  // 16384^2 f64); lbm_create sets it from the device's SM count
     bool tb_force = false;        // pair updates even on small lattices (tests)
     bool smem_attr_set = false;
     cudaStream_t stream = nullptr;
     // walls
     void *walls = nullptr;        // device table, element type T
     int64_t wall_rows = 0, wall_cap = 0, row_len = 0;
+    // ramp: per-update scale of the velocity entries of a wall row (lbm_set_ramp); d_one = device scalar 1
+    void *d_ramp = nullptr, *d_one = nullptr;
+    int64_t ramp_n = 0, ramp_cap = 0, ramp_it0 = 0;
+    int wave_tail = -1;           // stepw_kernel: width of the short chunks at the end of a launch (-1 = auto, 0 = uniform chunks)
+    // peer halo exchange (slab runs, one process per GPU; lbm_peer_*)
+    struct Peer {
+        bool attached = false, ipc = false;
+        void *buf[2] = {nullptr, nullptr};   // the neighbour's population buffers, mapped here
+        unsigned int *flags = nullptr;       // the neighbour's flag words
+        int64_t nxl = 0, plane = 0, origin = 0;
+    } peer[2];                    // 0 = left neighbour (x0 - 1), 1 = right neighbour
+    unsigned int *d_flags = nullptr;   // [0] written by the left neighbour, [1] by the right one, [2] time-out word
+    unsigned int peer_seq = 0, peer_waited = 0;
+    int64_t peer_timeout_ms = 20000;
     // macro
     void *rho = nullptr, *u = nullptr;
     bool macro_valid = false;
@@ -90,6 +107,8 @@ struct lbm_handle {
     // forces
     double *d_forces = nullptr;
     int64_t force_cap = 0, force_n = 0;
+    bool force_skip0 = false;     // slot 0 of the last lbm_step was a collide-only update (no link blocks ran)
+    double *d_force_now = nullptr;     // [n_obs][2] scratch of lbm_forces_now
     std::vector<double> force_const;   // f32 deviation storage: sum over an obstacle's owned links of 2 w_q c_q
     void *d_probe = nullptr;
     int64_t probe_cap = 0;
@@ -194,6 +213,45 @@ static int ensure_forces(lbm_handle *h, int64_t n)
     return LBM_OK;
 }
 
+// Slab runs with peer halos: before a launch reads the halo columns (or stores into a neighbour's), both
+// neighbours must have published the sequence number of the last update group (lbm_peer_signal).
+static int peer_wait(lbm_handle *h)
+{
+    if (h->peer_waited == h->peer_seq || !(h->peer[0].attached || h->peer[1].attached)) return LBM_OK;
+    peer_wait_kernel<<<1, 1, 0, h->stream>>>(h->d_flags, h->peer[0].attached ? 1 : 0, h->peer[1].attached ? 1 : 0,
+                                             h->peer_seq, h->d_flags + 2, (unsigned long long)h->peer_timeout_ms * 1000000ull);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->peer_waited = h->peer_seq;
+    return LBM_OK;
+}
+
+static void peer_detach(lbm_handle *h)
+{
+    for (auto &pe : h->peer) {
+        if (pe.attached && pe.ipc) {
+            for (void *b : pe.buf) if (b) cudaIpcCloseMemHandle(b);
+            if (pe.flags) cudaIpcCloseMemHandle(pe.flags);
+        }
+        pe = lbm_handle::Peer();
+    }
+}
+
+// Wall row index r of the API -> profile row of the table and device address of its ramp factor.  Without a
+// ramp table: row r, factor 1.  With one (lbm_set_ramp): factor ramp[r - it0], profile row r % wall_rows (one
+// base row serves every update).
+template <typename T> static const T *wall_row_ptr(const lbm_handle *h, int64_t row)
+{
+    if (!h->walls) return nullptr;
+    const int64_t pr = h->ramp_n > 0 ? row % h->wall_rows : row;
+    return static_cast<const T *>(h->walls) + pr * h->row_len;
+}
+template <typename T> static const T *wall_scale_ptr(const lbm_handle *h, int64_t row)
+{
+    if (h->ramp_n > 0) return static_cast<const T *>(h->d_ramp) + (row - h->ramp_it0);
+    return static_cast<const T *>(h->d_one);
+}
+
 template <typename T> static void fill_params(const lbm_handle *h, StepParams<T> &p, LinkParams &lp,
                                                int src, int dst, int xa, int xb, int64_t row, int64_t slot)
 {
@@ -223,10 +281,14 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.coef.a_opp = T(0.5 * (op - om));
     p.coef.a_eq = T(0.5 * (op + om));
     p.coef.wp0 = T(op * 4.0 / 9.0); p.coef.wp1 = T(op / 9.0); p.coef.wp5 = T(op / 36.0);
+    p.coef.wh0 = T(1.5 * op * 4.0 / 9.0); p.coef.wh1 = T(1.5 * op / 9.0); p.coef.wh5 = T(1.5 * op / 36.0);
     p.coef.wq1 = T(4.5 * op / 9.0); p.coef.wq5 = T(4.5 * op / 36.0);
+    p.coef.cs = T(0.5 * (1.0 - op)); p.coef.cd = T(0.5 * (1.0 - om));
     p.coef.wm1 = T(3.0 * om / 9.0); p.coef.wm5 = T(3.0 * om / 36.0);
-    p.walls = h->walls ? static_cast<const T *>(h->walls) + row * h->row_len : nullptr;
+    p.walls = wall_row_ptr<T>(h, row);
+    p.scale = wall_scale_ptr<T>(h, row);
     p.walls2 = nullptr;
+    p.scale2 = p.scale;
     p.rho_out = static_cast<T *>(h->rho);
     p.u_out = static_cast<T *>(h->u);
     p.uy_out = h->u ? static_cast<T *>(h->u) + (size_t)h->cfg.nxl * h->lay.pitch : nullptr;
@@ -234,8 +296,12 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.right_pressure = h->cfg.right_wall == LBM_RIGHT_PRESSURE;
     p.write_macro = 0;
     p.pf_ahead = h->pf_ahead;
-    for (int k = 0; k < 4; k++) p.wrow[k] = nullptr;
+    for (int k = 0; k < 4; k++) { p.wrow[k] = nullptr; p.wscale[k] = p.scale; }
     p.chunk = h->wave_chunk;
+    p.n_main = 1 << 30;
+    p.chunk_tail = h->wave_chunk;
+    p.peer_l = p.peer_r = nullptr;
+    p.peer_plane_l = p.peer_plane_r = 0;
     lp.n_cells = h->n_cells;
     lp.n_links = h->n_links;
     lp.n_obs = h->n_obs;
@@ -256,7 +322,8 @@ static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64
     StepParams<T> p;
     LinkParams lp;
     fill_params<T>(h, p, lp, src, dst, xa, xb, row1, 0);
-    p.walls2 = static_cast<const T *>(h->walls) + row2 * h->row_len;
+    p.walls2 = wall_row_ptr<T>(h, row2);
+    p.scale2 = wall_scale_ptr<T>(h, row2);
     // a corner cell reads its x-neighbour's pulled populations from shared memory: the right wall
     // column must not be the first column of its tile -> give the last two columns their own launch
     if (p.x_wr >= xa + 1 && p.x_wr < xb && (p.x_wr - xa) % TX == 0) {
@@ -271,6 +338,7 @@ static int launch_step2_v(lbm_handle *h, int src, int dst, int xa, int xb, int64
     }
     dim3 grid((unsigned)((h->cfg.ny + TY - 1) / TY), (unsigned)((xb - xa + TX - 1) / TX)), block(NT);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one temporal-blocking launch");
+    { int rcw = peer_wait(h); if (rcw) return rcw; }
     step2_kernel<T, STRICT, TX, TY, NT, CPT, MINB><<<grid, block, smem, h->stream>>>(p);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -344,7 +412,7 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
     StepParams<T> p;
     LinkParams lp;
     fill_params<T>(h, p, lp, src, dst, xa, xb, rows[0], 0);
-    for (int k = 0; k < D; k++) p.wrow[k] = static_cast<const T *>(h->walls) + rows[k] * h->row_len;
+    for (int k = 0; k < D; k++) { p.wrow[k] = wall_row_ptr<T>(h, rows[k]); p.wscale[k] = wall_scale_ptr<T>(h, rows[k]); }
     // columns that exist in the global lattice; without a wall the slab continues into the halo
     p.x_lo = h->cfg.x0 == 0 ? 0 : -(1 << 20);
     p.x_hi = h->cfg.x0 + h->cfg.nxl == h->cfg.nx ? (int)h->cfg.nxl : (int)h->cfg.nxl + (1 << 20);
@@ -385,11 +453,42 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
         chunk = std::min(chunk, std::max(n, 16));
     }
     while (n > chunk && n % chunk == 1) chunk++;
+    // The launch ends when its last block does, and the hardware hands blocks out in grid order (strip
+    // fastest, chunk slowest): the last chunks of the slab are made short -- at least one full set of
+    // resident blocks of a quarter of the width -- so that the SMs run dry within a short block's time
+    // (a 4096-column slab at 8 GPUs is only ~15 sets of resident blocks of 0.15-0.3 ms each).
+    int n_main = (n + chunk - 1) / chunk, chunk_tail = chunk, n_chunks = n_main;
+    const int tail_w = h->wave_tail < 0 ? (h->wave_auto ? std::max(32, chunk / 4) : 0) : h->wave_tail;
+    if (tail_w >= 16 && tail_w < chunk && n >= 4 * chunk) {
+        const int ntc = (int)std::max<long long>(1, (slots + strips - 1) / strips);
+        const int tail_cols = std::min(ntc * tail_w, n / 4);
+        const int nm = std::max(1, (n - tail_cols + chunk / 2) / chunk);
+        const int cm = (n - tail_cols + nm - 1) / nm;          // main chunks, all full
+        const int rest = n - nm * cm;
+        if (rest >= 2) {
+            int ct = std::min(tail_w, rest);
+            while (rest > ct && rest % ct == 1) ct++;
+            chunk = cm; n_main = nm; chunk_tail = ct;
+            n_chunks = nm + (rest + ct - 1) / ct;
+        }
+    }
     p.chunk = chunk;
-    int rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
+    p.n_main = n_main;
+    p.chunk_tail = chunk_tail;
+    // slab runs: the last stage also stores the kHalo edge columns into the neighbours' halos
+    for (int side = 0; side < 2; side++) {
+        const lbm_handle::Peer &pe = h->peer[side];
+        if (!pe.attached) continue;
+        T *base = static_cast<T *>(pe.buf[dst]) + pe.origin;
+        if (side == 0) { p.peer_l = base + pe.nxl * h->lay.pitch; p.peer_plane_l = pe.plane; }
+        else           { p.peer_r = base - h->cfg.nxl * h->lay.pitch; p.peer_plane_r = pe.plane; }
+    }
+    int rc = peer_wait(h);
+    if (rc) return rc;
+    rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
     if (rc) return rc;
     constexpr int TO = W::TO;
-    dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)((n + chunk - 1) / chunk)), block(D * kWaveRows + 32);
+    dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)n_chunks), block(D * kWaveRows + 32);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one wavefront launch");
     kern<<<grid, block, smem, h->stream>>>(p, h->tmap[src]);
     h->launches++;
@@ -451,6 +550,7 @@ static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int 
         }
         return LBM_OK;
     }
+    { int rcw = peer_wait(h); if (rcw) return rcw; }
     switch (mode) {
     case kFused: step_kernel<T, STRICT, kFused><<<grid, block, 0, h->stream>>>(p, lp); break;
     case kCollideOnly: step_kernel<T, STRICT, kCollideOnly><<<grid, block, 0, h->stream>>>(p, lp); break;
@@ -495,9 +595,17 @@ int lbm_create(const lbm_cfg *cfg, lbm_t **out)
     h->esz = (size_t)h->lay.elem_size;
     h->row_len = 5 * cfg->ny + 4 * cfg->nx;
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (h->n_sm < 1) h->n_sm = 148;
+    h->pf_ahead = 2 * h->n_sm;
     cudaError_t e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
-    if (e != cudaSuccess) { delete h; return fail(LBM_E_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_one, 8);
+    if (e == cudaSuccess) {
+        const double one_d = 1.0;
+        const float one_f = 1.0f;
+        e = cudaMemcpy(h->d_one, cfg->dtype == LBM_F64 ? (const void *)&one_d : (const void *)&one_f, h->esz, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { delete h; return fail(LBM_E_CUDA, "lbm_create: %s", cudaGetErrorString(e)); }
     *out = h;
     return LBM_OK;
 }
@@ -505,7 +613,8 @@ int lbm_create(const lbm_cfg *cfg, lbm_t **out)
 static void free_links(lbm_handle *h)
 {
     void *ptrs[] = {h->d_cell_x, h->d_cell_y, h->d_cell_off, h->d_link_q, h->d_link_kind, h->d_link_slot,
-                    h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask};
+                    h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask, h->d_force_now};
+    h->d_force_now = nullptr;
     for (void *p : ptrs) if (p) cudaFree(p);
     h->d_cell_x = h->d_cell_y = h->d_cell_off = h->d_link_q = h->d_link_kind = h->d_link_slot = h->d_obs_off = nullptr;
     h->d_link_c = nullptr; h->d_link_f = nullptr; h->d_done = nullptr; h->d_mask = nullptr;
@@ -524,6 +633,10 @@ int lbm_destroy(lbm_t *h)
     if (h->u) cudaFree(h->u);
     if (h->d_forces) cudaFree(h->d_forces);
     if (h->d_probe) cudaFree(h->d_probe);
+    if (h->d_ramp) cudaFree(h->d_ramp);
+    if (h->d_one) cudaFree(h->d_one);
+    peer_detach(h);
+    if (h->d_flags) cudaFree(h->d_flags);
     free_links(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -583,6 +696,11 @@ int lbm_sync(lbm_t *h)
 {
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_flags && (h->peer[0].attached || h->peer[1].attached)) {
+        unsigned int err = 0;
+        CUDA_TRY(cudaMemcpy(&err, h->d_flags + 2, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", err);
+    }
     return LBM_OK;
 }
 
@@ -804,6 +922,7 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     }
     CUDA_TRY(cudaMalloc(&h->d_link_f, std::max<size_t>((size_t)K, 1) * 2 * sizeof(double)));
     CUDA_TRY(cudaMemset(h->d_link_f, 0, std::max<size_t>((size_t)K, 1) * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_force_now, (size_t)n_obstacles * 2 * sizeof(double)));   // lbm_forces_now's own slot
     CUDA_TRY(cudaMalloc(&h->d_done, sizeof(unsigned int)));
     CUDA_TRY(cudaMemset(h->d_done, 0, sizeof(unsigned int)));
     // per-cell mask: cells owned by the link blocks are skipped by the bulk threads
@@ -844,8 +963,64 @@ int lbm_set_walls(lbm_t *h, int64_t n_rows, const double *rows_host)
 
 static int check_row(lbm_handle *h, int64_t row)
 {
+    if (h->ramp_n > 0) {          // ramp table: row = iteration index into it, profile row = row % wall_rows
+        if (!h->walls || h->wall_rows < 1) return fail(LBM_E_INVALID, "no wall profiles set");
+        if (row < h->ramp_it0 || row >= h->ramp_it0 + h->ramp_n)
+            return fail(LBM_E_INVALID, "row %lld outside the ramp table [%lld, %lld)", (long long)row, (long long)h->ramp_it0, (long long)(h->ramp_it0 + h->ramp_n));
+        return LBM_OK;
+    }
     if (!h->walls || row < 0 || row >= h->wall_rows)
         return fail(LBM_E_INVALID, "wall row %lld not in the table (%lld rows set)", (long long)row, (long long)h->wall_rows);
+    return LBM_OK;
+}
+
+int lbm_set_wall_profiles(lbm_t *h, const double *u_left, const double *u_right, const double *u_top,
+                          const double *u_bot, const double *rho_right)
+{
+    CHECK_H(h);
+    const int64_t nx = h->cfg.nx, ny = h->cfg.ny;
+    std::vector<double> row((size_t)h->row_len, 0.0);
+    if (u_left) memcpy(row.data(), u_left, 2 * ny * sizeof(double));
+    if (u_right) memcpy(row.data() + 2 * ny, u_right, 2 * ny * sizeof(double));
+    if (u_top) memcpy(row.data() + 4 * ny, u_top, 2 * nx * sizeof(double));
+    if (u_bot) memcpy(row.data() + 4 * ny + 2 * nx, u_bot, 2 * nx * sizeof(double));
+    if (rho_right) memcpy(row.data() + 4 * ny + 4 * nx, rho_right, ny * sizeof(double));
+    int rc = lbm_set_walls(h, 1, row.data());
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));    // `row` is a local
+    return LBM_OK;
+}
+
+int lbm_set_ramp(lbm_t *h, const double *ret_host, int64_t it0, int64_t n)
+{
+    CHECK_H(h);
+    if (n < 0 || (n > 0 && !ret_host)) return fail(LBM_E_INVALID, "bad ramp table");
+    if (n == 0) {
+        if (h->ramp_n) invalidate_graphs(h);
+        h->ramp_n = 0;
+        return LBM_OK;
+    }
+    if (n > h->ramp_cap) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        invalidate_graphs(h);
+        if (h->d_ramp) CUDA_TRY(cudaFree(h->d_ramp));
+        h->d_ramp = nullptr;
+        h->ramp_cap = 0;
+        const int64_t cap = std::max<int64_t>(n, 64);
+        CUDA_TRY(cudaMalloc(&h->d_ramp, (size_t)cap * h->esz));
+        h->ramp_cap = cap;
+    }
+    if (h->ramp_n == 0 || h->ramp_it0 != it0) invalidate_graphs(h);   // captured launches hold &ramp[row - it0]
+    if (h->cfg.dtype == LBM_F64) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_ramp, ret_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        std::vector<float> tmp((size_t)n);
+        for (int64_t k = 0; k < n; k++) tmp[k] = (float)ret_host[k];
+        CUDA_TRY(cudaMemcpyAsync(h->d_ramp, tmp.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->ramp_n = n;
+    h->ramp_it0 = it0;
     return LBM_OK;
 }
 
@@ -864,7 +1039,7 @@ static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, 
         const int64_t plain = n_updates - s - ((flags & LBM_STEP_MACRO_LAST) ? 1 : 0);
         // ... and the lattice is large enough to profit: below two full waves of 8 x 64 tiles at 4
         // blocks per SM the single-update kernel is faster (small lattices are latency bound)
-        const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * 148 || h->tb_force;
+        const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * (int64_t)h->n_sm || h->tb_force;
         if (h->temporal && big && mode == kFused && h->n_obs == 0 && plain >= 2 && h->cfg.nxl >= 4) {
             int d = (int)std::min<int64_t>(plain, h->depth);
             // wavefront launches pay off from ~4096^2 cells per slab (measured: 4096^2 93 vs 81 GLUPS for
@@ -910,6 +1085,7 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         if (rc) return rc;
         if (row_stride == 0) break;
     }
+    h->force_skip0 = h->kind == kHaveG;         // a collide-only first update runs no link blocks: slot 0 stays as it is
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     // Small lattices are launch bound (4 us per update at 200 x 200, profiles/README.md): a batch of
     // updates is captured once into a CUDA graph and replayed (the wall table, force slots and
@@ -917,7 +1093,7 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     // (<= 2^19 cells: below the size at which multi-update kernels take over, so that a captured batch
     // consists of step_kernel launches only)
     const bool graph_ok = h->use_graph && h->stream != nullptr && h->kind == kHaveF && n_updates >= 16 &&
-                          h->cfg.nxl * h->cfg.ny <= (1LL << 19);
+                          h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached;
     if (graph_ok) {
         lbm_handle::StepGraph *g = nullptr;
         for (auto &e : h->graphs)
@@ -1019,6 +1195,12 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->wave_rows = (int)value;
         h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
+    } else if (!strcmp(key, "wave_tail")) {
+        if (value != -1 && value != 0 && (value < 16 || value > (1 << 20))) return fail(LBM_E_INVALID, "wave_tail must be -1 (auto), 0 (off) or >= 16 columns");
+        h->wave_tail = (int)value;
+    } else if (!strcmp(key, "peer_timeout_ms")) {
+        if (value < 1) return fail(LBM_E_INVALID, "peer_timeout_ms must be positive");
+        h->peer_timeout_ms = value;
     } else if (!strcmp(key, "pf_ahead")) {
         if (value < 0 || value > (1 << 20)) return fail(LBM_E_INVALID, "pf_ahead must be in [0, 2^20]");
         h->pf_ahead = (int)value;
@@ -1058,6 +1240,7 @@ int lbm_apply_bc(lbm_t *h, int64_t row)
     if (rc) return rc;
     h->other_has_g = true;
     h->force_n = 1;
+    h->force_skip0 = false;
     return LBM_OK;
 }
 
@@ -1070,8 +1253,10 @@ int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
     CUDA_TRY(cudaMemcpyAsync(out, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!h->force_const.empty())
-        for (int64_t s = 0; s < n; s++)
+        for (int64_t s = 0; s < n; s++) {
+            if (first + s == 0 && h->force_skip0) continue;      // never produced by link blocks
             for (int k = 0; k < 2 * nobs; k++) out[s * 2 * nobs + k] += h->force_const[k];
+        }
     return LBM_OK;
 }
 
@@ -1082,9 +1267,7 @@ int lbm_forces_now(lbm_t *h, double *out)
     if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_forces_now needs post-collision populations");
     const int nobs = std::max(h->n_obs, 1);
     if (h->n_obs == 0) { out[0] = out[1] = 0.0; return LBM_OK; }
-    // uses a private slot past the step slots
-    double *d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, (size_t)nobs * 2 * sizeof(double)));
+    double *d_out = h->d_force_now;     // the handle's own slot (allocated with the links), not a step slot
     int rc = LBM_OK;
     {
         const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
@@ -1110,7 +1293,6 @@ int lbm_forces_now(lbm_t *h, double *out)
         if (!rc && !h->force_const.empty())
             for (int k = 0; k < 2 * nobs; k++) out[k] += h->force_const[k];
     }
-    cudaFree(d_out);
     return rc;
 }
 
@@ -1217,6 +1399,152 @@ int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_host, h->d_probe, (size_t)3 * n * h->esz, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+// ---- peer halo exchange (slab runs, one process per GPU) --------------------------------------
+int lbm_peer_export(lbm_t *h, lbm_peer_info *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(LBM_E_INVALID, "out is NULL");
+    if (h->buf[0] && !h->own_buf)
+        return fail(LBM_E_STATE, "peer halos need library-owned population buffers (do not call lbm_bind_state)");
+    int rc = ensure_state(h);
+    if (rc) return rc;
+    if (!h->d_flags) {
+        CUDA_TRY(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(h->d_flags, 0, 4 * sizeof(unsigned int)));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof *out);
+    static_assert(sizeof(cudaIpcMemHandle_t) <= LBM_IPC_HANDLE_BYTES, "IPC handle size");
+    for (int b = 0; b < 2; b++) {
+        cudaIpcMemHandle_t mh;
+        CUDA_TRY(cudaIpcGetMemHandle(&mh, h->buf[b]));
+        memcpy(out->mem[b], &mh, sizeof mh);
+        out->addr[b] = (uint64_t)(uintptr_t)h->buf[b];
+    }
+    cudaIpcMemHandle_t fh;
+    CUDA_TRY(cudaIpcGetMemHandle(&fh, h->d_flags));
+    memcpy(out->flags, &fh, sizeof fh);
+    out->flags_addr = (uint64_t)(uintptr_t)h->d_flags;
+    out->pid = (int64_t)getpid();
+    out->device = h->cfg.device;
+    out->x0 = h->cfg.x0; out->nxl = h->cfg.nxl;
+    out->origin = h->lay.origin; out->plane = h->lay.plane; out->pitch = h->lay.pitch; out->elem_size = h->lay.elem_size;
+    return LBM_OK;
+}
+
+int lbm_peer_attach(lbm_t *h, int32_t side, const lbm_peer_info *nb)
+{
+    CHECK_H(h);
+    if (side != 0 && side != 1) return fail(LBM_E_INVALID, "side must be 0 (left) or 1 (right)");
+    if (!nb) return fail(LBM_E_INVALID, "neighbour info is NULL");
+    if (!h->d_flags || !h->own_buf) return fail(LBM_E_STATE, "call lbm_peer_export on this handle first");
+    lbm_handle::Peer &pe = h->peer[side];
+    if (pe.attached) return fail(LBM_E_STATE, "side %d already attached", side);
+    if (nb->pitch != h->lay.pitch || nb->elem_size != h->lay.elem_size)
+        return fail(LBM_E_INVALID, "neighbour has a different row pitch or element type");
+    if (side == 0 ? nb->x0 + nb->nxl != h->cfg.x0 : nb->x0 != h->cfg.x0 + h->cfg.nxl)
+        return fail(LBM_E_INVALID, "neighbour slab [%lld, %lld) does not touch side %d of [%lld, %lld)", (long long)nb->x0,
+                    (long long)(nb->x0 + nb->nxl), side, (long long)h->cfg.x0, (long long)(h->cfg.x0 + h->cfg.nxl));
+    if (nb->nxl < kHalo || h->cfg.nxl < kHalo) return fail(LBM_E_INVALID, "slabs must be at least %d columns wide", kHalo);
+    if (nb->pid == (int64_t)getpid()) {     // same process (two handles on two devices): plain peer access
+        if (nb->device != h->cfg.device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess((int)nb->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail(LBM_E_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", (int)nb->device, cudaGetErrorString(e));
+        }
+        pe.buf[0] = (void *)(uintptr_t)nb->addr[0];
+        pe.buf[1] = (void *)(uintptr_t)nb->addr[1];
+        pe.flags = (unsigned int *)(uintptr_t)nb->flags_addr;
+        pe.ipc = false;
+    } else {
+        cudaIpcMemHandle_t mh;
+        for (int b = 0; b < 2; b++) {
+            memcpy(&mh, nb->mem[b], sizeof mh);
+            CUDA_TRY(cudaIpcOpenMemHandle(&pe.buf[b], mh, cudaIpcMemLazyEnablePeerAccess));
+        }
+        memcpy(&mh, nb->flags, sizeof mh);
+        void *fp = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&fp, mh, cudaIpcMemLazyEnablePeerAccess));
+        pe.flags = static_cast<unsigned int *>(fp);
+        pe.ipc = true;
+    }
+    pe.nxl = nb->nxl; pe.plane = nb->plane; pe.origin = nb->origin;
+    pe.attached = true;
+    invalidate_graphs(h);
+    return LBM_OK;
+}
+
+int lbm_peer_detach(lbm_t *h)
+{
+    CHECK_H(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    peer_detach(h);
+    return LBM_OK;
+}
+
+int lbm_peer_push(lbm_t *h, int32_t which)
+{
+    CHECK_H(h);
+    if (which != 0 && which != 1) return fail(LBM_E_INVALID, "which must be 0 (current) or 1 (other buffer)");
+    if (!(h->peer[0].attached || h->peer[1].attached)) return LBM_OK;
+    int rc = peer_wait(h);
+    if (rc) return rc;
+    const int b = h->cur ^ which;
+    const int64_t pitch = h->lay.pitch, nxl = h->cfg.nxl;
+    dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), 9 * 2 * kHalo), block(kBlock);
+    auto go = [&](auto zero) {
+        using T = decltype(zero);
+        T *pl = nullptr, *pr = nullptr;
+        if (h->peer[0].attached) pl = static_cast<T *>(h->peer[0].buf[b]) + h->peer[0].origin + h->peer[0].nxl * pitch;
+        if (h->peer[1].attached) pr = static_cast<T *>(h->peer[1].buf[b]) + h->peer[1].origin - nxl * pitch;
+        peer_push_kernel<T><<<grid, block, 0, h->stream>>>(static_cast<const T *>(elem_ptr(h, b, 0)), pl, pr, h->lay.plane,
+                                                           h->peer[0].plane, h->peer[1].plane, (int)pitch, (int)nxl, (int)h->cfg.ny);
+    };
+    if (h->cfg.dtype == LBM_F64) go(double(0)); else go(float(0));
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+int lbm_peer_signal(lbm_t *h)
+{
+    CHECK_H(h);
+    if (!(h->peer[0].attached || h->peer[1].attached)) return LBM_OK;
+    h->peer_seq++;
+    // I am the RIGHT neighbour of my left neighbour: its flag word [1]; and the left neighbour of my right one: [0]
+    peer_signal_kernel<<<1, 1, 0, h->stream>>>(h->peer[0].attached ? h->peer[0].flags + 1 : nullptr,
+                                               h->peer[1].attached ? h->peer[1].flags + 0 : nullptr, h->peer_seq);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LBM_OK;
+}
+
+int lbm_state_checksum(lbm_t *h, uint64_t *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(LBM_E_INVALID, "out is NULL");
+    if (h->kind == kNone) return fail(LBM_E_STATE, "no populations set");
+    if (!h->d_probe || h->probe_cap < 4) {
+        if (h->d_probe) { CUDA_TRY(cudaStreamSynchronize(h->stream)); CUDA_TRY(cudaFree(h->d_probe)); h->d_probe = nullptr; }
+        CUDA_TRY(cudaMalloc(&h->d_probe, 64));
+        h->probe_cap = 64 / (int64_t)h->esz;
+    }
+    unsigned long long *d = static_cast<unsigned long long *>(h->d_probe);
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof *d, h->stream));
+    const int blocks = 8 * h->n_sm;
+    if (h->cfg.dtype == LBM_F64)
+        checksum_kernel<double><<<blocks, kBlock, 0, h->stream>>>(static_cast<const double *>(elem_ptr(h, h->cur, 0)), h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, d);
+    else
+        checksum_kernel<float><<<blocks, kBlock, 0, h->stream>>>(static_cast<const float *>(elem_ptr(h, h->cur, 0)), h->lay.plane, (int)h->lay.pitch, (int)h->cfg.nxl, (int)h->cfg.ny, d);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *out = (uint64_t)v;
     return LBM_OK;
 }
 

@@ -483,13 +483,23 @@ class lattice:
         count) to an .npz file.  Valid after a completed set_bc."""
         if self._state != "streamed":
             raise C.LbmError(-3, "save_checkpoint() must follow set_bc")
+        obs = self._obstacles
+        off = np.cumsum([0] + [len(o.boundary) for o in obs]).astype(np.int64)
+        ijq = (np.concatenate([np.asarray(o.boundary).reshape(-1, 3) for o in obs]).astype(np.int64)
+               if obs else np.zeros((0, 3), dtype=np.int64))
+        ibb = (np.concatenate([np.asarray(o.ibb, dtype=np.float64).reshape(-1) for o in obs])
+               if obs else np.zeros(0))
         np.savez(path, F=self.g_up, row=self._row, updates=self.updates, right_wall=self._right_wall,
-                 bcs=np.array(sorted(self._bcs)), dtype=self.dtype)
+                 bcs=np.array(sorted(self._bcs)), dtype=self.dtype, link_offsets=off, link_ijq=ijq, link_ibb=ibb,
+                 link_tags=np.array([getattr(o, "tag", k + 1) for k, o in enumerate(obs)], dtype=np.int64),
+                 use_ibb=bool(self.IBB))
 
-    def load_checkpoint(self, path):
+    def load_checkpoint(self, path, obstacles=None):
         """Restore a state written by save_checkpoint; continue with app.set_inlets / lattice.macro()
-        of the next iteration.  Obstacles are re-recorded by the next set_bc; until then the links
-        uploaded last stay in force, so call this on a lattice that ran the same app."""
+        of the next iteration.  The obstacle link lists are part of the checkpoint: the first update
+        after loading bounces back on them exactly as the uninterrupted run does (the next set_bc
+        re-records the app's own obstacle objects).  obstacles: the app's obstacle objects in bounce-back
+        order, if drag_lift() is to find them by identity before the next set_bc."""
         z = np.load(path)
         F = np.ascontiguousarray(z["F"], dtype=self._np)
         if F.shape != (9, self.nx, self.ny):
@@ -502,6 +512,26 @@ class lattice:
         self.updates = int(z["updates"])
         self._state = "streamed"
         self._cache = {}
+        if "link_offsets" in z.files:
+            off = z["link_offsets"]
+            if obstacles is None:
+                class _Obs:          # minimal obstacle record (obstacle.py:3-25): the two kernel inputs
+                    pass
+                obstacles = []
+                for k in range(len(off) - 1):
+                    o = _Obs()
+                    o.boundary = z["link_ijq"][off[k]:off[k + 1]]
+                    o.ibb = z["link_ibb"][off[k]:off[k + 1]]
+                    o.tag = int(z["link_tags"][k])
+                    obstacles.append(o)
+            elif [len(o.boundary) for o in obstacles] != list(np.diff(off)):
+                raise ValueError("obstacles do not match the link lists of the checkpoint")
+            self.IBB = bool(z["use_ibb"])
+            self._obstacles = list(obstacles)
+            self._links_key = None
+        elif obstacles is not None:
+            self._obstacles = list(obstacles)
+            self._links_key = None
 
     def save_state(self):
         """Device-side copy of the current post-collision populations (for exact stop-rule rollback)."""
@@ -510,13 +540,17 @@ class lattice:
         src = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
         if getattr(self, "_saved", None) is None:
             self._saved = self._torch.empty_like(src)
-        self._saved.copy_(src)
+        # on the library's stream: ordered after the updates already enqueued and before the next ones
+        # (a copy on torch's current stream would race with them: the handle's stream is non-blocking)
+        with self._torch.cuda.stream(self._stream):
+            self._saved.copy_(src)
 
     def restore_state(self):
         cur = C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
         dst = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
-        dst.copy_(self._saved)
+        with self._torch.cuda.stream(self._stream):
+            dst.copy_(self._saved)
         self._cache = {}
 
     # ------------------------------------------------------------------------------------

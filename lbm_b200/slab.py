@@ -11,9 +11,19 @@ interface exchanges the three populations that cross it:
 
 Multi-update launches need deeper halos (see _plan and exchange_packed), obstacles two whole
 columns.  The update itself is the same kernel with the same per-cell arithmetic, so a slab run
-is bitwise identical to a single-GPU run.  For single- and two-update launches the edge columns
-are updated first and their exchange (NCCL send/recv on a high-priority side stream) overlaps the
-interior update; a wavefront launch covers the slab in one go and the exchange follows it.
+is bitwise identical to a single-GPU run.
+
+Two exchange mechanisms (SlabSolver(exchange=...)):
+
+  "peer"  (default on CUDA)  the neighbours' population buffers are mapped into this process (CUDA IPC,
+          lbm_peer_* of include/lbm_b200.h).  A wavefront launch stores its four edge columns straight
+          into the neighbour's halo columns from its last pipeline stage (NVLink peer stores, fused with
+          the compute); single- and two-update launches are followed by one small copy kernel that does
+          the same.  Ordering between the ranks is a pair of flag words per interface, written and
+          polled on the device: no host, no NCCL and no staging copies in the loop.
+  "nccl"  the halo columns travel as NCCL send/recv pairs on a high-priority side stream; for single-
+          and two-update launches the edge columns are updated first and their exchange overlaps the
+          interior update; a wavefront launch covers the slab in one go and the exchange follows it.
 """
 import numpy as np
 
@@ -140,22 +150,34 @@ class SlabSolver:
     """One rank's share of a slab-decomposed run (CUDA + NCCL)."""
 
     def __init__(self, nx, ny, tau, dist, rank, world, device, dtype="f64", arith="fused",
-                 right_wall="velocity", overlap=True):
+                 right_wall="velocity", overlap=True, exchange="peer"):
         import torch
         from .solver import Solver
         self.torch, self.dist = torch, dist
         self.rank, self.world = rank, world
         self.nx, self.ny = nx, ny
         self.x0, self.nxl = slab_bounds(nx, world, rank)
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.peer = exchange == "peer" and world > 1
         self.compute = torch.cuda.Stream(device=device)
         # the halo exchange must not queue behind the thousands of pending blocks of the interior
         # launch: high-priority stream, its kernels take the next free SM slots
         self.comm = torch.cuda.Stream(device=device, priority=-1)
         self.s = Solver(nx, ny, tau=tau, dtype=dtype, arith=arith, right_wall=right_wall,
-                        device=device, x0=self.x0, nxl=self.nxl, stream=self.compute)
+                        device=device, x0=self.x0, nxl=self.nxl, stream=self.compute, own_buffers=self.peer)
         if world > 1 and self.nxl < self.s.layout.halo:
             raise ValueError("slab of %d columns is narrower than the halo (%d)" % (self.nxl, self.s.layout.halo))
-        self.overlap = overlap and world > 1 and self.nxl >= 4
+        if self.peer:
+            # every rank publishes the IPC handles of its buffers and flag words; each maps its two neighbours
+            infos = [None] * world
+            dist.all_gather_object(infos, self.s.peer_export())
+            if rank > 0:
+                self.s.peer_attach(0, infos[rank - 1])
+            if rank + 1 < world:
+                self.s.peer_attach(1, infos[rank + 1])
+            dist.barrier()
+        self.overlap = overlap and world > 1 and self.nxl >= 4 and not self.peer
         self._halo_ready = None
         self.edge = 16                   # columns of the edge launches of update2 (one tile)
         self.updates = 0
@@ -189,6 +211,36 @@ class SlabSolver:
     def set_walls(self, rows):
         self.s.set_walls(rows)
 
+    def close(self):
+        """Unmap the neighbours' buffers before anybody frees them (collective)."""
+        if self.s is None:
+            return
+        self.finish()
+        if self.peer:
+            self.dist.barrier()
+            self.s.peer_detach()
+            self.dist.barrier()
+        self.s.close()
+        self.s = None
+
+    def _group_done(self):
+        """Peer mode: end of one update group (launches + pushes): signal the neighbours, flip."""
+        self.s.peer_signal()
+        self.s.flip()
+
+    def sync_halos(self):
+        """Fill the neighbours' halos of the CURRENT array (after set_post_collision / a restart)."""
+        if self.world == 1:
+            return
+        if self.peer:
+            self.s.peer_push(0)
+            self.s.peer_signal()
+        else:
+            cur, _ = self.s.views()
+            ev = self.torch.cuda.Event()
+            ev.record(self.compute)
+            self._exchange(cur, ev, self.s.layout.halo)
+
     def _exchange(self, oth, after, depth):
         torch = self.torch
         self.comm.wait_event(after)
@@ -213,18 +265,27 @@ class SlabSolver:
             s.flip()
             self.updates += 1
             return
+        if self.peer:
+            s.step_columns(0, nxl, row, slot)
+            s.peer_push(1)                                  # my four edge columns -> the neighbours' halos
+            self._group_done()
+            self.updates += 1
+            return
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)       # halos of the current array have landed
         _, oth = s.views()
         ev = torch.cuda.Event()
+        # the exchange that follows copies my last `next_depth` columns (2 with obstacles): the edge launches
+        # must cover all of them before `ev`, or the copy would race with the interior launch
+        w = max(2, next_depth)
         if self.n_obs:
             s.step_columns(0, nxl, row, slot)               # link blocks ride along with the whole slab
             ev.record(self.compute)
-        elif self.overlap:
-            s.step_columns(0, 2, row)
-            s.step_columns(nxl - 2, nxl, row)
+        elif self.overlap and nxl >= 4 * w:
+            s.step_columns(0, w, row)
+            s.step_columns(nxl - w, nxl, row)
             ev.record(self.compute)
-            s.step_columns(2, nxl - 2, row)
+            s.step_columns(w, nxl - w, row)
         else:
             s.step_columns(0, nxl, row)
             ev.record(self.compute)
@@ -241,11 +302,17 @@ class SlabSolver:
             s.flip()
             self.updates += 2
             return
+        if self.peer:
+            s.step2_columns(0, nxl, row1, row2)
+            s.peer_push(1)
+            self._group_done()
+            self.updates += 2
+            return
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)
         _, oth = s.views()
         ev = torch.cuda.Event()
-        w = self.edge
+        w = max(self.edge, next_depth)
         if self.overlap and nxl >= 4 * w:
             s.step2_columns(0, w, row1, row2)
             s.step2_columns(nxl - w, nxl, row1, row2)
@@ -270,6 +337,11 @@ class SlabSolver:
             s.flip()
             self.updates += d
             return
+        if self.peer:
+            s.stepn_columns(0, nxl, rows)                   # the last stage stores the edge columns into the neighbours' halos
+            self._group_done()
+            self.updates += d
+            return
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)
         _, oth = s.views()
@@ -281,7 +353,7 @@ class SlabSolver:
         # A launch pays 3(d-1) pipeline fill/drain steps per chunk whatever its width, so the edges are
         # whole chunks of 256 columns where the slab is wide enough (8 columns cost 20 sweep steps, 256
         # cost 268), and the exchange still has the long interior launch to hide behind.
-        w = 256 if nxl >= 2048 else max(8, d)
+        w = 256 if nxl >= 2048 else max(8, d, next_depth)
         if self.overlap and self.overlap_wave and nxl >= 4 * w:
             s.stepn_columns(0, w, rows)
             s.stepn_columns(nxl - w, nxl, rows)
@@ -310,7 +382,7 @@ class SlabSolver:
     def finish(self):
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)
-        self.compute.synchronize()
+        self.s.sync()                 # the compute stream; in peer mode also reports a timed-out flag wait
         self.comm.synchronize()
 
     def gather_populations(self):

@@ -9,7 +9,7 @@ from . import _capi as C
 
 class Solver:
     def __init__(self, nx, ny, tau=None, om_p=None, om_m=None, dtype="f64", arith="fused",
-                 right_wall="velocity", device=0, x0=0, nxl=None, stream=None):
+                 right_wall="velocity", device=0, x0=0, nxl=None, stream=None, own_buffers=False):
         import torch
         if not torch.cuda.is_available():
             raise C.LbmError(-2, "no CUDA device: lbm_b200 has no CPU fallback")
@@ -36,14 +36,19 @@ class Solver:
         lay = self.layout
         self.device = torch.device("cuda", device)
         tdt = torch.float64 if dtype == "f64" else torch.float32
-        self.buffers = [torch.empty(lay.elems, dtype=tdt, device=self.device) for _ in range(2)]
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         if s.cuda_stream == 0:           # legacy default stream: no stream capture (CUDA graphs of batches)
             s = torch.cuda.Stream(device=self.device)
         self.stream = s
         C.check(self._L.lbm_set_stream(h, C.c_vp(s.cuda_stream)))
-        C.check(self._L.lbm_bind_state(h, C.c_vp(self.buffers[0].data_ptr()),
-                                       C.c_vp(self.buffers[1].data_ptr()), lay.elems * lay.elem_size))
+        if own_buffers:
+            # the library allocates the two population buffers itself (cudaMalloc): needed for the peer
+            # halo exchange, whose CUDA IPC handles must describe whole allocations
+            self.buffers = None
+        else:
+            self.buffers = [torch.empty(lay.elems, dtype=tdt, device=self.device) for _ in range(2)]
+            C.check(self._L.lbm_bind_state(h, C.c_vp(self.buffers[0].data_ptr()),
+                                           C.c_vp(self.buffers[1].data_ptr()), lay.elems * lay.elem_size))
         self.row_len = int(self._L.lbm_wall_row_len(h))
 
     # -- lifetime ---------------------------------------------------------------------
@@ -109,6 +114,52 @@ class Solver:
             C.check(self._L.lbm_set_walls(self._h, rows.shape[0], self._p(rows)))
             self._walls_keepalive = rows
 
+    def set_wall_profiles(self, u_left=None, u_right=None, u_top=None, u_bot=None, rho_right=None):
+        """Base wall profiles (one table row) from the reference's five arrays; None = zeros."""
+        def p(a, n):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+            assert a.size == n
+            return a, self._p(a)
+        keep = [p(u_left, 2 * self.ny), p(u_right, 2 * self.ny), p(u_top, 2 * self.nx), p(u_bot, 2 * self.nx),
+                p(rho_right, self.ny)]
+        C.check(self._L.lbm_set_wall_profiles(self._h, *[k[1] for k in keep]))
+
+    def set_ramp(self, ret, it0=0):
+        """Per-iteration scale of the wall velocity profiles: `row` arguments become iteration indices
+        it0 .. it0+len(ret)-1.  ret: float64 numpy array or pinned torch tensor (asynchronous copy); None
+        removes the table."""
+        if ret is None:
+            C.check(self._L.lbm_set_ramp(self._h, None, 0, 0))
+            self._ramp_keepalive = None
+        elif hasattr(ret, "data_ptr"):
+            C.check(self._L.lbm_set_ramp(self._h, C.c_vp(ret.data_ptr()), int(it0), int(ret.numel())))
+            self._ramp_keepalive = ret
+        else:
+            ret = np.ascontiguousarray(ret, dtype=np.float64).reshape(-1)
+            C.check(self._L.lbm_set_ramp(self._h, self._p(ret), int(it0), ret.size))
+            self._ramp_keepalive = ret
+
+    # -- peer halo exchange (slab runs) --------------------------------------------------
+    def peer_export(self):
+        info = C.LbmPeerInfo()
+        C.check(self._L.lbm_peer_export(self._h, ctypes.byref(info)))
+        return bytes(info)
+
+    def peer_attach(self, side, info_bytes):
+        info = C.LbmPeerInfo.from_buffer_copy(info_bytes)
+        C.check(self._L.lbm_peer_attach(self._h, int(side), ctypes.byref(info)))
+
+    def peer_detach(self):
+        C.check(self._L.lbm_peer_detach(self._h))
+
+    def peer_push(self, which=1):
+        C.check(self._L.lbm_peer_push(self._h, int(which)))
+
+    def peer_signal(self):
+        C.check(self._L.lbm_peer_signal(self._h))
+
     def set_right_wall(self, kind):
         C.check(self._L.lbm_set_right_wall(self._h, C.LBM_RIGHT_PRESSURE if kind == "pressure" else C.LBM_RIGHT_VELOCITY))
 
@@ -149,6 +200,12 @@ class Solver:
         ms = ctypes.c_float()
         C.check(self._L.lbm_last_step_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def checksum(self):
+        """Wrap-around 64-bit sum of the bit patterns of the current population array (owned cells)."""
+        v = ctypes.c_uint64()
+        C.check(self._L.lbm_state_checksum(self._h, ctypes.byref(v)))
+        return int(v.value)
 
     @property
     def launches(self):
@@ -196,6 +253,8 @@ class Solver:
     def views(self):
         """Torch views [9, nxl+2*halo, pitch] of (current, other) population buffers; column index =
         x + halo (the first and last `halo` columns are the halo)."""
+        if self.buffers is None:
+            raise C.LbmError(-3, "views() needs torch-owned buffers (own_buffers=False)")
         cur, oth = C.c_vp(), C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._h, ctypes.byref(cur), ctypes.byref(oth)))
         i = 0 if cur.value == self.buffers[0].data_ptr() else 1

@@ -19,6 +19,7 @@ def main():
     from lbm_b200.slab import SlabSolver
     from lbm_b200.solver import Solver
     n_upd = int(sys.argv[1])
+    exchange = sys.argv[2] if len(sys.argv) > 2 else "peer"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -34,7 +35,7 @@ def main():
         a = 1.0 - np.exp(-(it + 1.0) ** 2 / 50.0)
         rows[it, 0:ny] = 0.05 * a * 4.0 * yy * (1.0 - yy)   # parabolic inlet, pressure outlet
         rows[it, 4 * ny + 4 * nx:] = 1.0
-    s = SlabSolver(nx, ny, tau, dist, rank, world, local, right_wall="pressure")
+    s = SlabSolver(nx, ny, tau, dist, rank, world, local, right_wall="pressure", exchange=exchange)
     s.set_links(obstacles)
     straddles = bool((bnd[:, 0] < s.x0).any() and (bnd[:, 0] >= s.x0).any()) if rank == world // 2 else False
     s.init_equilibrium(1.0, 0.03, 0.0)                      # uniform flow: the cylinder feels a force from the first update
@@ -48,6 +49,7 @@ def main():
     F = s.gather_populations()
     flags = [None] * world
     dist.all_gather_object(flags, straddles)
+    s.close()
     ok, out = True, {}
     if rank == 0:
         one = Solver(nx, ny, tau=tau, device=local, right_wall="pressure")
@@ -61,7 +63,7 @@ def main():
         fref = one.forces(0, n_upd - 1)
         df = float(np.max(np.abs(forces - fref)))
         ok = bool(np.array_equal(F, ref)) and df < 1e-12 and any(flags) and float(np.max(np.abs(fref))) > 1e-6
-        out = {"ok": ok, "pop_equal": bool(np.array_equal(F, ref)), "max_force_diff": df, "world": world,
+        out = {"ok": ok, "exchange": exchange, "pop_equal": bool(np.array_equal(F, ref)), "max_force_diff": df, "world": world,
                "straddles": any(flags), "max_force": float(np.max(np.abs(fref)))}
         print(json.dumps(out), flush=True)
     dist.barrier()

@@ -11,30 +11,34 @@ from oracle import oracle as orc
 W = np.array([4. / 9.] + [1. / 9.] * 4 + [1. / 36.] * 4)
 
 
-def collide_fused_numpy(G, om_p, om_m):
-    """d2q9.cuh: collide_fused, expression by expression (without FMA contraction)."""
+def collide_fused_numpy(G, om_p, om_m, dev=False):
+    """d2q9.cuh: collide_fused, expression by expression (without FMA contraction); dev: deviation
+    storage (G = f - w, rho = 1 + sum)."""
     one_m_omp = 1.0 - om_p
-    a_self, a_opp = 1.0 - 0.5 * (om_p + om_m), 0.5 * (om_p - om_m)
+    cs, cd = 0.5 * (1.0 - om_p), 0.5 * (1.0 - om_m)
     wp = om_p * W                      # om_p w
+    wh = 1.5 * om_p * W                # 1.5 om_p w
     wq = 4.5 * om_p * W                # 4.5 om_p w
     wm = 3.0 * om_m * W                # 3 om_m w
-    s = (((G[0] + G[1]) + (G[2] + G[3])) + ((G[4] + G[5]) + (G[6] + G[7]))) + G[8]
-    d56, d78 = G[5] - G[6], G[7] - G[8]
-    mx = ((G[1] - G[2]) + d56) - d78
-    my = ((G[3] - G[4]) + d56) + d78
-    y = 1.0 / s
+    S = [G[1] + G[2], G[3] + G[4], G[5] + G[6], G[7] + G[8]]
+    D = [G[1] - G[2], G[3] - G[4], G[5] - G[6], G[7] - G[8]]
+    s = G[0] + ((S[0] + S[1]) + (S[2] + S[3]))
+    r = 1.0 + s if dev else s
+    mx = (D[0] + D[2]) - D[3]
+    my = (D[1] + D[2]) + D[3]
+    y = 1.0 / r
     ms = [mx, my, mx + my, my - mx]
-    h = 1.5 * (mx * mx + my * my)
+    m2 = mx * mx + my * my
     F = np.empty_like(G)
-    F[0] = (one_m_omp * G[0] + s * wp[0]) - (h * wp[0]) * y
+    F[0] = (one_m_omp * G[0] + s * wp[0]) - (m2 * wh[0]) * y
     for k in range(4):
         q, qb = 2 * k + 1, 2 * k + 2
-        K = wq[q] * (ms[k] * ms[k]) - h * wp[q]
-        M = wm[q] * ms[k]
-        rp = s * wp[q]
-        F[q] = K * y + (a_self * G[q] + ((rp + M) - a_opp * G[qb]))
-        F[qb] = K * y + (a_self * G[qb] + ((rp - M) - a_opp * G[q]))
-    return F, s, mx * y, my * y
+        K = wq[q] * (ms[k] * ms[k]) - m2 * wh[q]
+        Fs = K * y + (cs * S[k] + s * wp[q])
+        Fd = cd * D[k] + wm[q] * ms[k]
+        F[q] = Fs + Fd
+        F[qb] = Fs - Fd
+    return F, r, mx * y, my * y
 
 
 @pytest.mark.parametrize("tau", [0.505, 0.56, 0.62, 1.7])
@@ -69,25 +73,6 @@ def test_deviation_storage_is_the_same_update():
     G = W[:, None] * (1.0 + 0.03 * rng.standard_normal((9, 500)))
     F, r, ux, uy = collide_fused_numpy(G, om_p, om_m)
     H = G - W[:, None]
-    # collide_fused with dev = true, expression by expression
-    one_m_omp = 1.0 - om_p
-    a_self, a_opp = 1.0 - 0.5 * (om_p + om_m), 0.5 * (om_p - om_m)
-    wp, wq, wm = om_p * W, 4.5 * om_p * W, 3.0 * om_m * W
-    s = (((H[0] + H[1]) + (H[2] + H[3])) + ((H[4] + H[5]) + (H[6] + H[7]))) + H[8]
-    rho = 1.0 + s
-    d56, d78 = H[5] - H[6], H[7] - H[8]
-    mx, my = ((H[1] - H[2]) + d56) - d78, ((H[3] - H[4]) + d56) + d78
-    y = 1.0 / rho
-    ms = [mx, my, mx + my, my - mx]
-    h = 1.5 * (mx * mx + my * my)
-    Fh = np.empty_like(H)
-    Fh[0] = (one_m_omp * H[0] + s * wp[0]) - (h * wp[0]) * y
-    for k in range(4):
-        q, qb = 2 * k + 1, 2 * k + 2
-        K = wq[q] * (ms[k] * ms[k]) - h * wp[q]
-        M = wm[q] * ms[k]
-        rp = s * wp[q]
-        Fh[q] = K * y + (a_self * H[q] + ((rp + M) - a_opp * H[qb]))
-        Fh[qb] = K * y + (a_self * H[qb] + ((rp - M) - a_opp * H[q]))
+    Fh, rho, _, _ = collide_fused_numpy(H, om_p, om_m, dev=True)
     assert np.max(np.abs(rho - r)) < 1e-15
     assert np.max(np.abs((Fh + W[:, None]) - F)) < 1e-15     # a few ulps of the populations (0.03 .. 0.44)

@@ -206,3 +206,67 @@ def test_large_grid_against_oracle():
     orc.run_loop(lat_o, case_o, n_iters=12)
     for k in ("g", "g_up", "rho", "u"):
         assert rel(getattr(lat_g, k), getattr(lat_o, k)) < 1e-12, k
+
+
+@pytest.mark.parametrize("arith", ["strict", "fused"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_ramp_table_equals_explicit_wall_rows(arith, dtype):
+    """lbm_set_wall_profiles + lbm_set_ramp (8 bytes of host input per update) == lbm_set_walls with one whole
+    row per update, bit for bit in f64: the apps' wall profiles are ONE rounded product scalar x profile
+    (cavity.py:73 u_lbm*ret; turek.py:104 (ret*u_lbm)*poiseuille) and the kernel forms the same product.
+    Channel with parabolic inlet, pressure outlet and an IBB cylinder; single-update and multi-update launches."""
+    from lbm_b200.solver import Solver
+    z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+    nx, ny, n = 160, 30, 25
+    c = cases.Turek(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])])
+    shape = c.inlet_shape(None)
+    ret = np.array([cases.ramp(it, 15) * c.u_lbm for it in range(n)])
+    outs = []
+    for mode in ("rows", "ramp"):
+        for with_obs in (True, False):
+            s = Solver(nx, ny, tau=c.tau_lbm, right_wall="pressure", arith=arith, dtype=dtype)
+            if with_obs:
+                s.set_links(c.obstacles)
+            else:
+                s.set_temporal_blocking(-1)             # multi-update launches on this small lattice
+            s.init_equilibrium(1.0)
+            if mode == "rows":
+                rows = np.zeros((n, s.row_len))
+                for it in range(n):
+                    rows[it, 0:ny] = ret[it] * shape
+                    rows[it, 4 * ny + 4 * nx:] = 1.0
+                s.set_walls(rows)
+            else:
+                u_left = np.zeros((2, ny)); u_left[0] = shape
+                s.set_wall_profiles(u_left=u_left, rho_right=np.ones(ny))
+                s.set_ramp(ret, 0)
+            s.step(1)
+            s.step(n - 1, 1, 1, macro_last=True)
+            outs.append((s.populations("post_collision"), s.macro(), s.forces(0, n - 1) if with_obs else None))
+            s.close()
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        if dtype == "f64":
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1][1], b[1][1])
+            if a[2] is not None:
+                assert np.array_equal(a[2], b[2])
+        else:   # f32: float(ret) * float(profile) vs float(ret * profile)
+            assert rel(a[0], b[0].astype(np.float64)) < 2e-6
+    assert np.max(np.abs(outs[0][1][1])) > 1e-3
+
+
+def test_ramp_rows_outside_the_table_are_rejected():
+    from lbm_b200 import _capi as C
+    from lbm_b200.solver import Solver
+    s = Solver(40, 30, tau=0.6)
+    s.init_equilibrium(1.0)
+    s.set_wall_profiles(u_top=np.ones((2, 40)))
+    s.set_ramp(np.linspace(0, 1, 8), 100)
+    s.step(1, 100, 1)
+    s.step(4, 100, 1)
+    with pytest.raises(C.LbmError):
+        s.step(4, 106, 1)          # iterations 106..109: 108 and 109 are outside [100, 108)
+    with pytest.raises(C.LbmError):
+        s.step(1, 3, 1)
+    s.set_ramp(None)
+    s.step(2, 0, 0)                # back to plain rows (one row in the table)
+    s.close()

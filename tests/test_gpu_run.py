@@ -116,6 +116,53 @@ def test_checkpoint_restart_continues_bit_for_bit(tmp_path):
     assert np.array_equal(np.array(cb.forces[-40:]), np.array(ca.forces[-40:]))
 
 
+def test_checkpoint_restart_in_a_fresh_process_state(tmp_path):
+    """The real restart case: the checkpoint is loaded into a lattice that never ran the app (no obstacles
+    recorded, no links uploaded).  The link lists travel in the checkpoint, so the first update after loading
+    bounces back on the cylinder exactly as the uninterrupted run does."""
+    from lbm_b200.lattice import lattice
+    ca, cb, cc = _turek30(), _turek30(), _turek30()
+    la = lattice(ca, make_dirs=False)
+    orc.run_loop(la, ca, n_iters=100)
+    lb = lattice(cb, make_dirs=False)
+    orc.run_loop(lb, cb, n_iters=60)
+    ck = str(tmp_path / "state.npz")
+    lb.save_checkpoint(ck)
+    lb.close()
+    lc = lattice(cc, make_dirs=False)           # fresh: nothing initialised, nothing recorded
+    lc.load_checkpoint(ck)
+    for it in range(60, 100):
+        cc.set_inlets(lc, it)
+        lc.macro(); lc.equilibrium(); lc.collision_stream(); cc.set_bc(lc)
+        cc.observables(lc, it)
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lc, k), getattr(la, k)), k
+    assert np.array_equal(np.array(cc.forces), np.array(ca.forces[-40:]))
+
+
+def test_stop_rule_rollback_on_a_lattice_where_launches_take_long():
+    """save_state / restore_state are ordered on the library's stream: the exact-stop rollback of the
+    batched driver on a lattice large enough for a batch to be still running when the host gets to the copy."""
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+
+    class Stop(cases.Cavity):
+        stop = "obs"
+
+        def observables(self, lat, it):
+            self.seen = it
+
+        def check_stop(self, it):
+            return it < 37
+    cg, co = Stop(L_lbm=1536, sigma=10), Stop(L_lbm=1536, sigma=10)
+    lg = lattice(cg, make_dirs=False, arith="strict")
+    n = run(lg, cg, batch=24, quiet=True)
+    lo = orc.OracleLattice(co)
+    n_ref = orc.run_loop(lo, co)
+    assert n == n_ref == 38
+    assert np.array_equal(lg.g_up, lo.g_up)
+
+
 def test_graph_replay_equals_plain_launches():
     """Batches of >= 16 updates on small lattices are captured into a CUDA graph and replayed
     (lbm_step); populations, stored drag/lift sums and the macro fields must not notice."""

@@ -152,6 +152,70 @@ def test_batched_cavity_against_oracle_bitwise():
         assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
 
 
+@pytest.mark.parametrize("arith", ["strict", "fused"])
+def test_depth4_launches_directly_against_the_oracle(arith):
+    """The benchmarked kernel against the oracle without a detour over step_kernel: 2048 x 2048 cavity,
+    the collide-only update + 16 updates as FOUR four-update launches with the default chunk / strip
+    geometry (what lbm_step picks for config 5), ramped lid.  STRICT arithmetic: every array equals the
+    oracle bit for bit; FUSED (production): within 1e-12 of max|ref| (BASELINE.json north_star)."""
+    from lbm_b200.lattice import lattice
+    n = 2048
+    cg, co = cases.Cavity(L_lbm=n, sigma=6, tau_lbm=0.56, u_lbm=0.1), cases.Cavity(L_lbm=n, sigma=6, tau_lbm=0.56, u_lbm=0.1)
+    lg = lattice(cg, make_dirs=False, arith=arith)
+    cg.initialize(lg)
+    cg.set_inlets(lg, 0)
+    lg.macro(); lg.equilibrium(); lg.collision_stream(); cg.set_bc(lg)          # iteration 0 (collide-only) + BC record
+    rows = []
+    for it in range(16):                                                        # update it+1 applies the walls of iteration it
+        cg.set_inlets(lg, it)
+        rows.append(lg.snapshot_walls())
+    from lbm_b200 import _capi as C
+    L, h = lg._L, lg._h
+    C.check(L.lbm_set_temporal_blocking(h, -1))          # multi-update launches also below 2^24 cells
+    C.check(L.lbm_set_temporal_depth(h, 4))
+    l0 = L.lbm_launch_count(h)
+    lg.batch_updates(np.stack(rows))                                            # 15 plain updates (4 + 4 + 4 + 3) + the macro update
+    launches = L.lbm_launch_count(h) - l0
+    assert launches == 5, launches
+    lg.collision_stream()
+    cg.set_inlets(lg, 16)
+    cg.set_bc(lg)
+    lo = orc.OracleLattice(co)
+    orc.run_loop(lo, co, n_iters=17)
+    for k in ("g_up", "g", "rho", "u"):
+        a, b = getattr(lg, k), getattr(lo, k)
+        if arith == "strict":
+            assert np.array_equal(a, b), k
+        else:
+            assert float(np.max(np.abs(a - b)) / np.max(np.abs(b))) < 1e-12, k
+    lg.close()
+
+
+def test_short_tail_chunks_are_bit_identical():
+    """Non-uniform chunk widths (short chunks at the end of a wavefront launch, "wave_tail") change the
+    schedule, not the result; right wall in the last (short) chunk, several widths incl. a one-column rest."""
+    from lbm_b200.solver import Solver
+    nx, ny = 331, 150
+    outs = []
+    for tail in (0, 16, 17, 24, 26):
+        s = Solver(nx, ny, tau=0.58, arith="strict", right_wall="pressure")
+        rng = np.random.default_rng(3)
+        g = (np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)[:, None, None]
+             * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
+        s.set_populations(g)
+        s.set_walls(_rows(nx, ny, 8, 5, True))
+        s.set_temporal_blocking(0)
+        s.step(1)
+        s.set_tuning("wave_chunk", 64)
+        s.set_tuning("wave_tail", tail)
+        s.stepn_columns(0, nx, [0, 1, 2, 3]); s.flip()
+        s.stepn_columns(0, nx, [4, 5, 6, 7]); s.flip()
+        outs.append(s.populations("post_collision"))
+        s.close()
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+
+
 def test_full_size_multi_update_launch_checksum():
     """BASELINE config 5 size (32768 x 32768 f64, 154.6 GB): eight updates with four-update launches,
     with two-update launches and with single-update launches leave bit-identical populations
@@ -181,6 +245,7 @@ def test_full_size_multi_update_launch_checksum():
         sums = [float(v[q].sum(dtype=torch.float64)) for q in range(9)]
         bits = [int(v[q].view(torch.int64).sum()) for q in range(9)]      # wrap-around sum of the bit patterns
         edge = v[:, :, -1].clone().cpu().numpy(), v[:, 0, :].clone().cpu().numpy()
+        assert s.checksum() == sum(bits) & 0xFFFFFFFFFFFFFFFF          # lbm_state_checksum == the same sum by torch
         launches = s.launches - l0
         s.close()
         del cur, v
