@@ -59,9 +59,11 @@ template <typename T> struct StepParams {
     // peer_X + q*peer_plane_X + xc*pitch + y  is the neighbour's copy of my cell (q, xc, y).
     T *peer_l, *peer_r;
     long long peer_plane_l, peer_plane_r;
+    int peer_nxl_l;         // width of the left neighbour's slab (its halo column of my column xc is peer_nxl_l + xc)
     // non-uniform chunks: blockIdx.y < n_main sweeps `chunk` columns, later blocks `chunk_tail` columns
     // (short blocks at the end of the launch shorten its tail)
     int n_main, chunk_tail;
+    int wave_l2;            // stepw_kernel: columns of L2 prefetch ahead of the TMA ring (0 = off)
 };
 
 struct LinkParams {
@@ -464,6 +466,23 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0,
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(b)) : "memory");
 }
 
+// TMA tile copy shared -> global of a dense box; part of the issuing thread's current bulk async-group.
+__device__ __forceinline__ void tma_store_3d(const void *tmap, const void *src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// L2 prefetch of a box (no shared memory, no completion tracking): brings a column in from HBM many steps before
+// the ring has a free slot for it, so that the later tensor load hits in L2
+__device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 struct alignas(64) TensorMap { unsigned long long opaque[16]; };   // CUtensorMap (cuda.h), built by the host
 
 // Geometry of a strip.  The TMA unit wants the box to start on a 16-byte boundary along the
@@ -481,7 +500,11 @@ template <typename T, int TYB, int D> struct Wave {
     static constexpr int R = 4;                         // slots of the rings between stages
     static constexpr int LAG = 2;                       // columns between consecutive stages
     static constexpr int HDR = 128;                     // mbarriers
-    static constexpr size_t smem(int R0) { return HDR + ((size_t)R0 * COL0 + (size_t)(D - 1) * R * COL) * sizeof(T); }
+    // staging ring of the last stage: NSTG dense slots [9][TO] that TMA tensor stores copy to global memory
+    static constexpr int NSTG = 3;
+    static constexpr int STG = (9 * TO * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
+    static __host__ __device__ constexpr size_t stg_off(int R0) { return (HDR + ((size_t)R0 * COL0 + (size_t)(D - 1) * R * COL) * sizeof(T) + 127) / 128 * 128; }
+    static __host__ __device__ constexpr size_t smem(int R0) { return stg_off(R0) + (size_t)NSTG * STG * sizeof(T); }
     static_assert(TO > 0 && TO % AL == 0 && (PAD + M0) % AL == 0 && M0 >= 1 && (2 * M0) % AL == 0, "strip geometry");
 };
 
@@ -520,7 +543,9 @@ __device__ __noinline__ void wall_cell(const StepParams<T> &p, const T *walls, c
 
 template <typename T, bool STRICT, int D, int TYB, int R0, int MINB>
 __global__ void __launch_bounds__(D * TYB + 32, MINB)
-stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ TensorMap tmap)
+stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ TensorMap tmap,
+             const __grid_constant__ TensorMap tmap_st, const __grid_constant__ TensorMap tmap_pl,
+             const __grid_constant__ TensorMap tmap_pr)
 {
     using A = Ar<T, STRICT>;
     using W = Wave<T, TYB, D>;
@@ -532,6 +557,8 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wave_smem);
     T *lvl0 = reinterpret_cast<T *>(wave_smem + W::HDR);     // [R0][COL0]         level 0 (TMA ring)
     T *lvl = lvl0 + R0 * COL0;                               // [D-1][R][9][ROWS]  levels 1 .. D-1
+    T *stg = reinterpret_cast<T *>(wave_smem + W::stg_off(R0));   // [NSTG][9][TO]     output columns of the last stage
+    constexpr int NSTG = W::NSTG, STG = W::STG;
 
     const int stage = threadIdx.x / TYB, t = threadIdx.x - stage * TYB;
     const int ys = (int)blockIdx.x * TO - PAD, y = ys + t;
@@ -549,31 +576,71 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     }
     __syncthreads();
 
-    // ---- producer warp: one lane streams the level-0 columns in, five columns ahead of stage 0 ----
+    // slab runs: this chunk's share of the kHalo edge columns also goes to the neighbour's halo (peer memory)
+    const bool push_l = p.peer_l != nullptr && ca < kHalo, push_r = p.peer_r != nullptr && cb > p.nxl - kHalo;
+
+    // ---- producer warp: one lane streams the level-0 columns in, five columns ahead of stage 0, and sends the
+    // columns the last stage has finished to global memory: ONE tensor copy per column in either direction ----
     if (threadIdx.x >= NC) {
         auto load_column = [&](int c) {                      // tensor coordinates: (row, column + halo, plane)
             unsigned long long *b = mbar + (c & (R0 - 1));
             mbar_expect_tx(b, 9u * ROWS * (unsigned)sizeof(T));
             tma_load_3d(lvl0 + (c & (R0 - 1)) * COL0, &tmap, ys - M0, c + kHalo, 0, b);
         };
-        if (threadIdx.x == NC)
+        // column xc of the last stage sits in staging slot `slot` (dense [9][TO], rows ys+PAD ..): one tensor store into
+        // the destination buffer -- rows beyond ny are clipped by the map -- and, for the kHalo edge columns of a
+        // slab, one more into the neighbour's halo (NVLink peer store)
+        auto store_column = [&](int xc, int slot) {
+            const T *src = stg + slot * STG;
+            tma_store_3d(&tmap_st, src, ys + PAD, xc + kHalo, 0);
+            if (push_l && xc < kHalo) tma_store_3d(&tmap_pl, src, ys + PAD, p.peer_nxl_l + xc + kHalo, 0);
+            if (push_r && xc >= p.nxl - kHalo) tma_store_3d(&tmap_pr, src, ys + PAD, xc - p.nxl + kHalo, 0);
+            tma_commit();
+        };
+        const int l2 = p.wave_l2;                            // columns of L2 look-ahead beyond the ring (0 = off)
+        if (threadIdx.x == NC) {
             for (int c = c_first; c < c_first + R0 && c <= c_last; c++) load_column(c);
+            for (int c = c_first + R0; c < c_first + R0 + l2 && c <= c_last; c++) tma_prefetch_3d(&tmap, ys - M0, c + kHalo, 0);
+            for (int i = 0; i < 4 && c_first + i <= c_last; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);   // step 0 reads columns xs0-1 .. xs0+1
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");          // level 0 is ready for step 0
+        // The last stage wrote column xl = xl0 + s - 1 into slot (s-1) % NSTG during step s-1.  A LEFT-wall column
+        // is completed one step late (its two corner cells are computed together with column x_wl + 1), so it is
+        // sent one iteration later, before the column that follows it.
+        const int xl0 = xs0 - LAG * (D - 1);
+        int slot = NSTG - 1, prev = NSTG - 2;                // slots of steps s-1 and s-2 (s = 0: none)
         for (int s = 0; s < nsteps; s++) {
-            // the ring holds columns x-2 .. x+R0-3 of stage 0's column x = xs0 + s; x-3 was last read in step s-1
-            if (threadIdx.x == NC && s >= 1 && xs0 + s + R0 - 3 <= c_last) load_column(xs0 + s + R0 - 3);
+            if (threadIdx.x == NC) {
+                // the ring holds columns x-2 .. x+R0-3 of stage 0's column x = xs0 + s; x-3 was last read in step s-1
+                if (s >= 1 && xs0 + s + R0 - 3 <= c_last) load_column(xs0 + s + R0 - 3);
+                if (l2 > 0 && s >= 1 && xs0 + s + R0 - 3 + l2 <= c_last) tma_prefetch_3d(&tmap, ys - M0, xs0 + s + R0 - 3 + l2 + kHalo, 0);
+                const int xl = xl0 + s - 1;
+                if (s >= 2 && xl - 1 == p.x_wl && xl - 1 >= ca && xl - 1 < cb) store_column(xl - 1, prev);
+                if (s >= 1 && xl != p.x_wl && xl >= ca && xl < cb) store_column(xl, slot);
+                tma_wait_read<1>();                          // every group but the newest has been read out of its slot
+                // the column stage 0 reads first in step s+1 (x+2): the compute threads never touch the mbarriers --
+                // a try_wait round trip at the head of every step made stage 0 the slowest stage (ncu: it waited
+                // least at the block barrier) -- the block barrier that ends step s publishes the data to them
+                const int c = xs0 + s + 2;
+                if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
+            }
+            prev = slot;
+            slot = slot == NSTG - 1 ? 0 : slot + 1;
             __syncwarp();                                    // (the barrier instruction wants the whole warp)
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
+        // (the last stage finishes D-1 steps before the sweep ends: nothing is left in the staging ring)
+        if (threadIdx.x == NC) tma_wait_read<0>();
         return;
     }
 
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");              // (the producer's: level 0 is ready for step 0)
     // stage k computes columns [ca - (D-1-k), cb + (D-1-k)) that exist in the global lattice
     const int lo = max(ca - (D - 1 - stage), p.x_lo), hi = min(cb + (D - 1 - stage), p.x_hi);
     const bool row_ok = y >= 0 && y < p.ny;
     const bool edge_row = y == 0 || y == p.ny - 1;
     const bool store_row = t >= PAD && t < PAD + TO;
-    // slab runs: this chunk's share of the kHalo edge columns also goes to the neighbour's halo (peer memory)
-    const bool push_l = p.peer_l != nullptr && ca < kHalo, push_r = p.peer_r != nullptr && cb > p.nxl - kHalo;
     const T *const in_base = (stage == 0 ? lvl0 : lvl + (stage - 1) * R * COL) + M0;
     const RingSource<T, ROWS> src{in_base, stage == 0 ? R0 - 1 : R - 1, stage == 0 ? COL0 : COL, ys};
     const T *const in_t = in_base + t;
@@ -592,20 +659,15 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
     auto sweep = [&](auto first_c, auto last_c) {
         constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
         constexpr int MASK = FIRST ? R0 - 1 : R - 1, STRIDE = FIRST ? COL0 : COL;
-        auto store = [&](int xc, const T (&G)[9]) {
+        // LAST: the column goes to the staging slot of its step (sl = slot of the current step; a deferred left
+        // corner belongs to the column of the step before); the producer warp sends the slot to global memory
+        auto store = [&](int xc, int x, int sl, const T (&G)[9]) {
             if (LAST) {
                 if (store_row) {
-                    const int idx = xc * p.pitch + y;
+                    const int k = xc == x ? sl : (sl == 0 ? NSTG - 1 : sl - 1);
+                    T *o = stg + k * STG + (t - PAD);
 #pragma unroll
-                    for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
-                    if (push_l && xc < kHalo) {
-#pragma unroll
-                        for (int q = 0; q < 9; q++) p.peer_l[q * p.peer_plane_l + idx] = G[q];
-                    }
-                    if (push_r && xc >= p.nxl - kHalo) {
-#pragma unroll
-                        for (int q = 0; q < 9; q++) p.peer_r[q * p.peer_plane_r + idx] = G[q];
-                    }
+                    for (int q = 0; q < 9; q++) o[q * TO] = G[q];
                 }
             } else {
                 T *o = out + (xc & (R - 1)) * COL;
@@ -615,13 +677,7 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
         };
         // one sweep step on column x: cm / c0 / cp = this thread's row in the ring slots of columns x-1 / x / x+1,
         // o = its row in the output slot of column x (unused by the last stage)
-        auto step = [&](int s, int x, const T *cm, const T *c0, const T *cp, T *o) {
-            if (FIRST) {
-                if (s == 0)
-                    for (int i = 0; i < 3; i++) mbar_wait(mbar + ((c_first + i) & (R0 - 1)), 0);
-                const int c = x + 1;
-                if (c <= c_last) mbar_wait(mbar + (c & (R0 - 1)), ((c - c_first) / R0) & 1);
-            }
+        auto step = [&](int s, int x, const T *cm, const T *c0, const T *cp, T *o, int sl) {
             if ((unsigned)(x - f_lo) < (unsigned)f_n) {
                 // bulk cell: pull, collide, store -- nothing else
                 T G[9], r, ux, uy;
@@ -632,7 +688,7 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                 }
                 collide_cell<A, T>(G, cf, false, r, ux, uy);
                 if (LAST) {
-                    store(x, G);
+                    store(x, x, sl, G);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 9; q++) o[q * ROWS] = G[q];
@@ -645,12 +701,15 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
                 for (; n > 0; n--, xc--) {
                     T G[9];
                     wall_cell<A, T>(p, walls, wscale, src, xc, y, G);
-                    store(xc, G);
+                    store(xc, x, sl, G);
                 }
             }
+            // the staging slot is read by the async proxy (TMA store) after the barrier
+            if (LAST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         };
-        int x = xs0 - LAG * stage, s = 0;
+        int x = xs0 - LAG * stage, s = 0, sl = 0;            // sl = s % NSTG (staging slot of the step, last stage)
+        auto next_slot = [&]() { if (LAST) sl = sl == NSTG - 1 ? 0 : sl + 1; };
         if (!FIRST) {
             // the 4-slot rings repeat every four columns: four steps per loop iteration with the slot
             // addresses kept in registers (no address arithmetic in the bulk path)
@@ -663,12 +722,17 @@ stepw_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ Te
             }
             for (; s + R <= nsteps; s += R, x += R) {
 #pragma unroll
-                for (int j = 0; j < R; j++) step(s + j, x + j, ib[(j + R - 1) & (R - 1)], ib[j], ib[(j + 1) & (R - 1)], ob[j]);
+                for (int j = 0; j < R; j++) {
+                    step(s + j, x + j, ib[(j + R - 1) & (R - 1)], ib[j], ib[(j + 1) & (R - 1)], ob[j], sl);
+                    next_slot();
+                }
             }
         }
-        for (; s < nsteps; s++, x++)
+        for (; s < nsteps; s++, x++) {
             step(s, x, in_t + ((x - 1) & MASK) * STRIDE, in_t + (x & MASK) * STRIDE, in_t + ((x + 1) & MASK) * STRIDE,
-                 out + (x & (R - 1)) * COL);
+                 out + (x & (R - 1)) * COL, sl);
+            next_slot();
+        }
     };
     using Yes = std::integral_constant<bool, true>;
     using No = std::integral_constant<bool, false>;

@@ -70,6 +70,9 @@ struct lbm_handle {
     bool wave_attr_set[5] = {false, false, false, false, false};
     int wave_occ[5] = {1, 1, 1, 1, 1};   // resident blocks per SM of stepw_kernel<.., D, ..>
     TensorMap tmap[2];            // one 3-D tensor map per population buffer (stepw_kernel's TMA loads)
+    TensorMap tmap_st[2];         // ... and one for its TMA stores (box = output rows of a strip x 1 column x 9 planes)
+    TensorMap tmap_peer[2][2];    // [side][buffer]: store maps into the neighbours' buffers (peer halo exchange)
+    int tmap_peer_rows = 0;
     int tmap_rows = 0;            // strip geometry (rows, depth) the maps were built for (0 = not built)
     int pf_ahead = 2 * 148;       // L2 prefetch distance of step2_kernel in blocks: two blocks per SM (+3.5 % measured at
                                   // 16384^2 f64); lbm_create sets it from the device's SM count
@@ -82,6 +85,7 @@ struct lbm_handle {
     // ramp: per-update scale of the velocity entries of a wall row (lbm_set_ramp); d_one = device scalar 1
     void *d_ramp = nullptr, *d_one = nullptr;
     int64_t ramp_n = 0, ramp_cap = 0, ramp_it0 = 0;
+    int wave_l2 = 6;              // stepw_kernel: columns of L2 prefetch ahead of the TMA ring
     int wave_tail = -1;           // stepw_kernel: width of the short chunks at the end of a launch (-1 = auto, 0 = uniform chunks)
     // peer halo exchange (slab runs, one process per GPU; lbm_peer_*)
     struct Peer {
@@ -298,10 +302,12 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.pf_ahead = h->pf_ahead;
     for (int k = 0; k < 4; k++) { p.wrow[k] = nullptr; p.wscale[k] = p.scale; }
     p.chunk = h->wave_chunk;
+    p.wave_l2 = h->wave_l2;
     p.n_main = 1 << 30;
     p.chunk_tail = h->wave_chunk;
     p.peer_l = p.peer_r = nullptr;
     p.peer_plane_l = p.peer_plane_r = 0;
+    p.peer_nxl_l = 0;
     lp.n_cells = h->n_cells;
     lp.n_links = h->n_links;
     lp.n_obs = h->n_obs;
@@ -374,10 +380,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int ensure_tensor_maps(lbm_handle *h, int rows_per_slot, int key /* strip rows and depth */)
+static int encode_map(const lbm_handle *h, TensorMap *out, void *base, int64_t rows, int64_t cols, int64_t plane, int box_rows)
 {
-    const int tyb = key;
-    if (h->tmap_rows == tyb) return LBM_OK;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -387,18 +391,44 @@ static int ensure_tensor_maps(lbm_handle *h, int rows_per_slot, int key /* strip
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     static_assert(sizeof(TensorMap) == sizeof(CUtensorMap), "TensorMap must mirror CUtensorMap");
-    const cuuint64_t dims[3] = {(cuuint64_t)h->lay.pitch, (cuuint64_t)(h->cfg.nxl + 2 * kHalo), 9};
-    const cuuint64_t strides[2] = {(cuuint64_t)h->lay.pitch * h->esz, (cuuint64_t)h->lay.plane * h->esz};
-    const cuuint32_t box[3] = {(cuuint32_t)rows_per_slot, 1, 9}, estr[3] = {1, 1, 1};
-    for (int b = 0; b < 2; b++) {
-        void *base = elem_ptr(h, b, -(int64_t)kHalo * h->lay.pitch);     // (q = 0, x = -halo, y = 0)
-        CUresult r = encode(reinterpret_cast<CUtensorMap *>(&h->tmap[b]),
-                            h->cfg.dtype == LBM_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                            3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    const cuuint64_t dims[3] = {(cuuint64_t)rows, (cuuint64_t)cols, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->lay.pitch * h->esz, (cuuint64_t)plane * h->esz};
+    const cuuint32_t box[3] = {(cuuint32_t)box_rows, 1, 9}, estr[3] = {1, 1, 1};
+    CUresult r = encode(reinterpret_cast<CUtensorMap *>(out),
+                        h->cfg.dtype == LBM_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LBM_E_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return LBM_OK;
+}
+
+// Load maps: box = all rows of a ring slot (margins included; rows outside the allocation's pitch are zero-filled).
+// Store maps: box = the output rows of a strip, tensor height = ny so that rows beyond the lattice are clipped.
+// Tensor column 0 = local column -halo.  The neighbours' maps describe THEIR buffers (peer memory).
+static int ensure_tensor_maps(lbm_handle *h, int rows_per_slot, int out_rows, int key /* strip rows and depth */)
+{
+    if (h->tmap_rows != key) {
+        for (int b = 0; b < 2; b++) {
+            void *base = elem_ptr(h, b, -(int64_t)kHalo * h->lay.pitch);     // (q = 0, x = -halo, y = 0)
+            int rc = encode_map(h, &h->tmap[b], base, h->lay.pitch, h->cfg.nxl + 2 * kHalo, h->lay.plane, rows_per_slot);
+            if (!rc) rc = encode_map(h, &h->tmap_st[b], base, h->cfg.ny, h->cfg.nxl + 2 * kHalo, h->lay.plane, out_rows);
+            if (rc) return rc;
+        }
+        h->tmap_rows = key;
+        h->tmap_peer_rows = 0;
     }
-    h->tmap_rows = tyb;
+    if (h->tmap_peer_rows != key) {
+        for (int side = 0; side < 2; side++) {
+            const lbm_handle::Peer &pe = h->peer[side];
+            for (int b = 0; b < 2; b++) {
+                if (!pe.attached) { h->tmap_peer[side][b] = h->tmap_st[b]; continue; }   // (never used: a valid placeholder)
+                void *base = static_cast<char *>(pe.buf[b]) + (pe.origin - (int64_t)kHalo * h->lay.pitch) * (int64_t)h->esz;
+                int rc = encode_map(h, &h->tmap_peer[side][b], base, h->cfg.ny, pe.nxl + 2 * kHalo, pe.plane, out_rows);
+                if (rc) return rc;
+            }
+        }
+        h->tmap_peer_rows = key;
+    }
     return LBM_OK;
 }
 
@@ -480,17 +510,17 @@ static int launch_stepw_v(lbm_handle *h, int src, int dst, int xa, int xb, const
         const lbm_handle::Peer &pe = h->peer[side];
         if (!pe.attached) continue;
         T *base = static_cast<T *>(pe.buf[dst]) + pe.origin;
-        if (side == 0) { p.peer_l = base + pe.nxl * h->lay.pitch; p.peer_plane_l = pe.plane; }
+        if (side == 0) { p.peer_l = base + pe.nxl * h->lay.pitch; p.peer_plane_l = pe.plane; p.peer_nxl_l = (int)pe.nxl; }
         else           { p.peer_r = base - h->cfg.nxl * h->lay.pitch; p.peer_plane_r = pe.plane; }
     }
     int rc = peer_wait(h);
     if (rc) return rc;
-    rc = ensure_tensor_maps(h, W::ROWS, kWaveRows * 8 + D);
+    rc = ensure_tensor_maps(h, W::ROWS, W::TO, kWaveRows * 8 + D);
     if (rc) return rc;
     constexpr int TO = W::TO;
     dim3 grid((unsigned)((h->cfg.ny + TO - 1) / TO), (unsigned)n_chunks), block(D * kWaveRows + 32);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "slab too wide for one wavefront launch");
-    kern<<<grid, block, smem, h->stream>>>(p, h->tmap[src]);
+    kern<<<grid, block, smem, h->stream>>>(p, h->tmap[src], h->tmap_st[dst], h->tmap_peer[0][dst], h->tmap_peer[1][dst]);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;
@@ -1195,6 +1225,9 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->wave_rows = (int)value;
         h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
+    } else if (!strcmp(key, "wave_l2")) {
+        if (value < 0 || value > 4096) return fail(LBM_E_INVALID, "wave_l2 must be in [0, 4096]");
+        h->wave_l2 = (int)value;
     } else if (!strcmp(key, "wave_tail")) {
         if (value != -1 && value != 0 && (value < 16 || value > (1 << 20))) return fail(LBM_E_INVALID, "wave_tail must be -1 (auto), 0 (off) or >= 16 columns");
         h->wave_tail = (int)value;
@@ -1473,6 +1506,7 @@ int lbm_peer_attach(lbm_t *h, int32_t side, const lbm_peer_info *nb)
     }
     pe.nxl = nb->nxl; pe.plane = nb->plane; pe.origin = nb->origin;
     pe.attached = true;
+    h->tmap_peer_rows = 0;
     invalidate_graphs(h);
     return LBM_OK;
 }
@@ -1482,6 +1516,7 @@ int lbm_peer_detach(lbm_t *h)
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     peer_detach(h);
+    h->tmap_peer_rows = 0;
     return LBM_OK;
 }
 

@@ -245,8 +245,8 @@ def test_full_size_multi_update_launch_checksum():
         sums = [float(v[q].sum(dtype=torch.float64)) for q in range(9)]
         bits = [int(v[q].view(torch.int64).sum()) for q in range(9)]      # wrap-around sum of the bit patterns
         edge = v[:, :, -1].clone().cpu().numpy(), v[:, 0, :].clone().cpu().numpy()
-        assert s.checksum() == sum(bits) & 0xFFFFFFFFFFFFFFFF          # lbm_state_checksum == the same sum by torch
         launches = s.launches - l0
+        assert s.checksum() == sum(bits) & 0xFFFFFFFFFFFFFFFF          # lbm_state_checksum == the same sum by torch
         s.close()
         del cur, v
         torch.cuda.empty_cache()
