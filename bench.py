@@ -399,11 +399,10 @@ def gpu_arm(args):
         m = min(depth, K - done)
         s.s.set_ramp(ramp_host[it:it + m], it)
         s.advance(it, m, depth)
-        s.finish()
-        line_y = s.s.probe_line(1, ymid, it + m - 1)             # row y = ny/2, this slab's columns
+        line_y = s.probe_line(1, ymid, it + m - 1)             # row y = ny/2, this slab's columns (waits for the launch)
         d2h = line_y.nbytes
         if owns_mid:
-            line_x = s.s.probe_line(0, xmid - s.x0, it + m - 1)  # column x = nx/2
+            line_x = s.probe_line(0, xmid - s.x0, it + m - 1)  # column x = nx/2
             d2h += line_x.nbytes
         it += m
         done += m

@@ -167,7 +167,7 @@ int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot
 int lbm_flip(lbm_t *h);
 /* Two consecutive updates (wall rows row1, row2) of local columns [xa, xb) in ONE launch
  * (temporal blocking through shared memory), without flipping; reads columns xa-2 .. xb+1.
- * Not available with obstacle links.  lbm_step pairs updates this way by itself when the lattice
+ * Not available with obstacle links (lbm_stepn_columns is).  lbm_step pairs updates this way by itself when the lattice
  * has no obstacles and is large enough to profit (>= 1184 tiles of 8 x 64 cells), unless
  * lbm_set_temporal_blocking(h, 0) was called; enable < 0 forces pairing on any size (tests). */
 int lbm_step2_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row1, int64_t row2);
@@ -175,7 +175,12 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
 /* depth = 2, 3 or 4 consecutive updates (wall rows rows[0..depth-1]) of local columns [xa, xb) in
  * ONE launch (wavefront temporal blocking: a block sweeps a strip of rows along x, the updates
  * form a pipeline through shared memory, the source is streamed in by TMA bulk copies), without
- * flipping; reads columns xa-depth .. xb+depth-1.  Not available with obstacle links.
+ * flipping; reads columns xa-depth .. xb+depth-1.  With obstacle links (nb_bounce_back_obstacle,
+ * nb.py:77-117; nb_drag_lift, nb.py:49-73) the call must cover the whole slab: the bodies get a band of
+ * columns of their own -- four columns beyond the outermost link cell on either side -- that is updated
+ * `depth` times by the single-update kernel with the links (momentum-exchange sums in force slots
+ * 0 .. depth-1) while one wavefront launch per side covers the obstacle-free columns; lbm_step groups
+ * updates the same way on lattices of >= 2^24 cells.  Bit-identical to single updates.
  * lbm_set_temporal_depth bounds the updates per launch that lbm_step chooses by itself
  * (1 = never more than one, 2 = step2_kernel pairs, 3/4 = wavefront launches; default 4). */
 int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int64_t *rows);

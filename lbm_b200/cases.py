@@ -19,8 +19,11 @@ import os
 
 import numpy as np
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                       "tests", "golden")
+# package data: the obstacle link lists of the BASELINE configurations (Turek cylinder at ny = 100 / 200, the
+# eight squares of the array case) as the reference's lattice.add_obstacle produces them (lattice.py:290-375)
+# from its shape generator; written by tests/golden/make_golden.py, reproduced by lbm_b200/geometry.py
+# (tests/test_geometry_cpu.py)
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 class ConvergenceBuffer:
@@ -183,14 +186,20 @@ class Channel(Case):
 
     right_wall = "pressure"
 
+    def poiseuille(self, pt):
+        """Inlet profile at a point (turek.py:165-173)."""
+        y = pt[1]
+        H = self.y_max - self.y_min
+        u = np.zeros(2)
+        u[0] = 4.0 * (self.y_max - y) * (y - self.y_min) / H ** 2
+        return u
+
     def inlet_shape(self, lattice):
         ny = self.ny
         dy = (self.y_max - self.y_min) / (ny - 1)        # lattice.get_coords, lattice.py:379-387
-        H = self.y_max - self.y_min
         prof = np.zeros(ny)
         for j in range(ny):
-            y = self.y_min + j * dy
-            prof[j] = 4.0 * (self.y_max - y) * (y - self.y_min) / H ** 2   # turek.py:165-173
+            prof[j] = self.poiseuille([self.x_min, self.y_min + j * dy])[0]
         return prof
 
     def set_inlets(self, lattice, it):
@@ -295,12 +304,11 @@ class Array(Channel):
 
 
 def load_links(path):
-    """Obstacle link lists stored by tests/golden/make_golden.py (outputs of the
-    reference's lattice.add_obstacle)."""
+    """Obstacle link lists of lbm_b200/data/ (outputs of the reference's lattice.add_obstacle)."""
     if isinstance(path, (list, tuple)):
         return list(path)
     if not os.path.isabs(path):
-        path = os.path.join(_GOLDEN, path)
+        path = os.path.join(_DATA, path)
     z = np.load(path)
     off = z["offsets"]
     return [Obstacle(z["boundary"][off[k]:off[k + 1]], z["ibb"][off[k]:off[k + 1]], tag=k + 1)

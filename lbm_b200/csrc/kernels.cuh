@@ -69,6 +69,7 @@ template <typename T> struct StepParams {
 struct LinkParams {
     int n_cells;            // distinct boundary cells in this slab
     int n_links;
+    int n_links_total;      // links of the caller's whole list (slots), this slab's or not
     int n_obs;
     const int *cell_x, *cell_y, *cell_off;   // [n_cells], [n_cells], [n_cells+1]
     const int *link_q;                       // [n_links] direction fluid -> solid
@@ -182,12 +183,22 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
 // ---------------------------------------------------------------------------------------
 // Obstacle links: one thread per distinct boundary cell (the extra blocks of the step kernel)
 // ---------------------------------------------------------------------------------------
+constexpr int kLinkLocal = 1024;     // per-link terms of up to this many links stay in the link block's shared memory
+
 template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
 __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
 {
     using A = Ar<T, STRICT>;
-    const int c = block * nthreads + threadIdx.x;
-    if (c < lp.n_cells) {
+    // Up to kLinkLocal links (every BASELINE config: 234 / 468 / 928) are handled by ONE block that keeps the
+    // per-link momentum-exchange terms in shared memory and reduces them after a block barrier: no fence,
+    // atomic and second trip through L2 on the critical path of the (latency-bound) small lattices.
+    __shared__ double sf[2 * kLinkLocal];
+    const bool local = lp.n_link_blocks == 1 && lp.n_links_total <= kLinkLocal;
+    if (local) {
+        for (int k = threadIdx.x; k < 2 * lp.n_links_total; k += nthreads) sf[k] = 0.0;   // (links of other slabs stay 0)
+        __syncthreads();
+    }
+    for (int c = block * nthreads + threadIdx.x; c < lp.n_cells; c += lp.n_link_blocks * nthreads) {
         const int x = lp.cell_x[c], y = lp.cell_y[c];
         const int idx = x * p.pitch + y;
         T G[9];
@@ -215,32 +226,37 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
             // sum_links 2 w_q c_q is added once, in double, on the host)
             const T g0 = A::add(a, val);
             const int s = lp.link_slot[l];
-            lp.link_f[2 * s] = (double)A::mul(g0, T(kCx[q]));
-            lp.link_f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
+            double *f = local ? sf : lp.link_f;
+            f[2 * s] = (double)A::mul(g0, T(kCx[q]));
+            f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
         }
         if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
     }
-    // last block done: fixed-order reduction of the per-link terms, per obstacle.  Warp w sums the links
-    // a + w*32 + lane + 256 k of the obstacle's range [a, b) (strided partial sums, then a shuffle
-    // tree), thread 0 adds the eight warp sums in warp order: no dependence on block scheduling, one
-    // barrier per pass of (up to) kObsPass obstacles instead of nine per obstacle.
+    // Fixed-order reduction of the per-link terms, per obstacle -- by this block if it is the only one, else by the
+    // last block to finish.  Warp w sums the links a + w*32 + lane + 256 k of the obstacle's range [a, b) (strided
+    // partial sums, then a shuffle tree), thread 0 adds the eight warp sums in warp order: no dependence on
+    // block scheduling, one barrier per pass of (up to) kObsPass obstacles instead of nine per obstacle.
     constexpr int kObsPass = 16;
     __shared__ bool last;
     __shared__ double red[kObsPass][kBlock / 32][2];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
+    if (!local) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+    } else {
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
     for (int o0 = 0; o0 < lp.n_obs; o0 += kObsPass) {
         const int no = min(kObsPass, lp.n_obs - o0);
         for (int o = 0; o < no; o++) {
             double fx = 0.0, fy = 0.0;
             for (int k = lp.obs_off[o0 + o] + threadIdx.x; k < lp.obs_off[o0 + o + 1]; k += nthreads) {
-                fx += __ldcg(lp.link_f + 2 * k);
-                fy += __ldcg(lp.link_f + 2 * k + 1);
+                fx += local ? sf[2 * k] : __ldcg(lp.link_f + 2 * k);
+                fy += local ? sf[2 * k + 1] : __ldcg(lp.link_f + 2 * k + 1);
             }
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) {
@@ -258,7 +274,7 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *lp.done = 0;
+    if (!local && threadIdx.x == 0) *lp.done = 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -94,7 +94,8 @@ struct lbm_handle {
         unsigned int *flags = nullptr;       // the neighbour's flag words
         int64_t nxl = 0, plane = 0, origin = 0;
     } peer[2];                    // 0 = left neighbour (x0 - 1), 1 = right neighbour
-    unsigned int *d_flags = nullptr;   // [0] written by the left neighbour, [1] by the right one, [2] time-out word
+    unsigned int *d_flags = nullptr;   // [0] written by the left neighbour, [1] by the right one
+    unsigned int *h_err = nullptr, *d_err = nullptr;   // time-out word of the flag waits: pinned host memory, mapped
     unsigned int peer_seq = 0, peer_waited = 0;
     int64_t peer_timeout_ms = 20000;
     // macro
@@ -108,6 +109,11 @@ struct lbm_handle {
     double *d_link_f = nullptr;
     unsigned int *d_done = nullptr;
     unsigned char *d_mask = nullptr;
+    // Obstacle band (multi-update launches on lattices with bodies): a child handle that owns local columns
+    // [band_ca, band_cb) of this slab with its own pair of buffers; band_a .. band_b are the columns it delivers
+    lbm_handle *band = nullptr;
+    bool is_band = false;
+    int band_a = 0, band_b = 0, band_ca = 0, band_cb = 0;
     // forces
     double *d_forces = nullptr;
     int64_t force_cap = 0, force_n = 0;
@@ -118,9 +124,10 @@ struct lbm_handle {
     int64_t probe_cap = 0;
     // CUDA graphs of whole lbm_step batches on small (launch-bound) lattices
     struct StepGraph {
-        int64_t n = 0, first_row = 0, stride = 0;
+        int64_t n = 0, first_row = 0, stride = 0, ramp_it0 = 0;
         uint32_t flags = 0;
         int cur0 = 0, cur1 = 0;
+        bool ramp = false;            // captured with a ramp table (&ramp[row - it0] baked in) or without (&one)
         int64_t launches = 0;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
@@ -223,7 +230,7 @@ static int peer_wait(lbm_handle *h)
 {
     if (h->peer_waited == h->peer_seq || !(h->peer[0].attached || h->peer[1].attached)) return LBM_OK;
     peer_wait_kernel<<<1, 1, 0, h->stream>>>(h->d_flags, h->peer[0].attached ? 1 : 0, h->peer[1].attached ? 1 : 0,
-                                             h->peer_seq, h->d_flags + 2, (unsigned long long)h->peer_timeout_ms * 1000000ull);
+                                             h->peer_seq, h->d_err, (unsigned long long)h->peer_timeout_ms * 1000000ull);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->peer_waited = h->peer_seq;
@@ -310,6 +317,7 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.peer_nxl_l = 0;
     lp.n_cells = h->n_cells;
     lp.n_links = h->n_links;
+    lp.n_links_total = h->n_links_total;
     lp.n_obs = h->n_obs;
     lp.cell_x = h->d_cell_x; lp.cell_y = h->d_cell_y; lp.cell_off = h->d_cell_off;
     lp.link_q = h->d_link_q; lp.link_kind = h->d_link_kind; lp.link_slot = h->d_link_slot;
@@ -603,6 +611,85 @@ static int launch_step(lbm_handle *h, int mode, int src, int dst, int xa, int xb
 }
 
 // ---------------------------------------------------------------------------------------
+// Obstacles and multi-update launches.  The wavefront kernel keeps three columns of the previous level in its
+// rings; an interpolated bounce-back link reads two columns away (nb.py:98-104), and the link cells are few.
+// So the bodies get a BAND of columns of their own: all link cells lie in [x_min, x_max]; the band delivers
+// columns [a, b) = [x_min - 4, x_max + 5) and is computed by a child handle that owns [a - 4, b + 4) (clipped at
+// the lattice walls) with its own pair of buffers and the same link lists: per group of D <= 4 updates its
+// columns are copied out of the source buffer, updated D times by step_kernel (link blocks ride along, drag/lift
+// sums go to the parent's force slots) -- no halo refresh, so the valid range shrinks by one column per update
+// and side and ends as [a, b) -- and copied into the destination buffer, while ONE wavefront launch per side
+// covers the obstacle-free columns [0, a) and [b, nxl).  Those launches recompute up to three columns inside
+// the band's margin at intermediate levels; the margin of four columns beyond the outermost link cell is what
+// keeps every cell they touch out of reach of a link for that many updates.  Same per-cell functions
+// everywhere, hence bit-identical to single updates (tests/test_gpu_temporal.py).
+static int build_band(lbm_handle *h, int32_t n_obstacles, const int64_t *offsets, const int64_t *ijq, const double *ibb,
+                      int32_t use_ibb, int xmin, int xmax)
+{
+    const int nxl = (int)h->cfg.nxl;
+    const bool wall_l = h->cfg.x0 == 0, wall_r = h->cfg.x0 + h->cfg.nxl == h->cfg.nx;
+    int a = xmin - kHalo, b = xmax + kHalo + 1;
+    if (a < 2) a = 0;                          // (a wavefront launch is at least two columns wide)
+    if (b > nxl - 2) b = nxl;
+    if ((a == 0 && !wall_l) || (b == nxl && !wall_r)) return LBM_OK;     // band on a slab interface: single updates only
+    if (h->peer[0].attached || h->peer[1].attached) return LBM_OK;
+    const int ca = std::max(a - kHalo, 0), cb = std::min(b + kHalo, nxl);
+    if (cb - ca < 2 || (a == 0 && b == nxl)) return LBM_OK;
+    lbm_cfg c = h->cfg;
+    c.x0 = h->cfg.x0 + ca;
+    c.nxl = cb - ca;
+    lbm_handle *child = nullptr;
+    int rc = lbm_create(&c, &child);
+    if (rc) return rc;
+    child->is_band = true;
+    child->stream = h->stream;
+    child->temporal = false;
+    child->use_graph = false;
+    rc = lbm_set_links(child, n_obstacles, offsets, ijq, ibb, use_ibb);
+    if (!rc) rc = ensure_state(child);
+    if (rc) { lbm_destroy(child); return rc; }
+    child->kind = kHaveF;
+    h->band = child;
+    h->band_a = a; h->band_b = b; h->band_ca = ca; h->band_cb = cb;
+    return LBM_OK;
+}
+
+static bool band_usable(const lbm_handle *h) { return h->band != nullptr && !h->peer[0].attached && !h->peer[1].attached; }
+
+// One group of d = 2..4 updates of the whole slab (src -> dst buffer), bodies in the band; force slots slot0 ..
+static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64_t *rows, int64_t slot0)
+{
+    lbm_handle *b = h->band;
+    const int64_t pitch = h->lay.pitch, esz = (int64_t)h->esz;
+    // the child shares the parent's wall table, ramp and force slots
+    b->walls = h->walls; b->wall_rows = h->wall_rows; b->wall_cap = 0;
+    b->d_ramp = h->d_ramp; b->ramp_n = h->ramp_n; b->ramp_it0 = h->ramp_it0; b->ramp_cap = 0;
+    b->d_forces = h->d_forces; b->force_cap = h->force_cap;
+    b->cfg.right_wall = h->cfg.right_wall;
+    b->stream = h->stream;
+    // 1. the band's columns out of the source buffer
+    for (int q = 0; q < 9; q++)     // (a column range of one plane is contiguous; planes may be > 2 GB apart: no 2-D copy)
+        CUDA_TRY(cudaMemcpyAsync(elem_ptr(b, b->cur, q * b->lay.plane), elem_ptr(h, src, q * h->lay.plane + (int64_t)h->band_ca * pitch),
+                                 (size_t)((h->band_cb - h->band_ca) * pitch * esz), cudaMemcpyDeviceToDevice, h->stream));
+    // 2. d single updates with the links
+    for (int k = 0; k < d; k++) {
+        int rc = launch_step(b, kFused, b->cur, b->cur ^ 1, 0, (int)b->cfg.nxl, rows[k], slot0 + k, false);
+        if (rc) return rc;
+        b->cur ^= 1;
+    }
+    h->launches += d;
+    // 3. the obstacle-free columns on either side: one wavefront launch each
+    if (h->band_a > 0) { int rc = launch_stepw(h, src, dst, 0, h->band_a, d, rows); if (rc) return rc; }
+    if (h->band_b < (int)h->cfg.nxl) { int rc = launch_stepw(h, src, dst, h->band_b, (int)h->cfg.nxl, d, rows); if (rc) return rc; }
+    // 4. the band's share of the result
+    for (int q = 0; q < 9; q++)
+        CUDA_TRY(cudaMemcpyAsync(elem_ptr(h, dst, q * h->lay.plane + (int64_t)h->band_a * pitch),
+                                 elem_ptr(b, b->cur, q * b->lay.plane + (int64_t)(h->band_a - h->band_ca) * pitch),
+                                 (size_t)((h->band_b - h->band_a) * pitch * esz), cudaMemcpyDeviceToDevice, h->stream));
+    return LBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 extern "C" {
 
 int lbm_abi_version(void) { return LBM_ABI_VERSION; }
@@ -651,11 +738,21 @@ static void free_links(lbm_handle *h)
     h->n_obs = h->n_cells = h->n_links = h->n_links_total = h->n_link_blocks = 0;
 }
 
+static void destroy_band(lbm_handle *h)
+{
+    if (!h->band) return;
+    lbm_handle *b = h->band;
+    h->band = nullptr;
+    b->walls = nullptr; b->d_ramp = nullptr; b->d_forces = nullptr;      // aliases of the parent's tables
+    lbm_destroy(b);
+}
+
 int lbm_destroy(lbm_t *h)
 {
     if (!h) return LBM_OK;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    destroy_band(h);
     invalidate_graphs(h);
     if (h->own_buf) { cudaFree(h->buf[0]); cudaFree(h->buf[1]); }
     if (h->walls) cudaFree(h->walls);
@@ -667,6 +764,7 @@ int lbm_destroy(lbm_t *h)
     if (h->d_one) cudaFree(h->d_one);
     peer_detach(h);
     if (h->d_flags) cudaFree(h->d_flags);
+    if (h->h_err) cudaFreeHost(h->h_err);
     free_links(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -726,11 +824,8 @@ int lbm_sync(lbm_t *h)
 {
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->d_flags && (h->peer[0].attached || h->peer[1].attached)) {
-        unsigned int err = 0;
-        CUDA_TRY(cudaMemcpy(&err, h->d_flags + 2, sizeof err, cudaMemcpyDeviceToHost));
-        if (err) return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", err);
-    }
+    if (h->h_err && *(volatile unsigned int *)h->h_err)
+        return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", *h->h_err);
     return LBM_OK;
 }
 
@@ -851,6 +946,7 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     free_links(h);
+    destroy_band(h);
     invalidate_graphs(h);
     h->force_const.clear();
     if (h->d_forces) { cudaFree(h->d_forces); h->d_forces = nullptr; h->force_cap = 0; }
@@ -928,7 +1024,8 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     coff.push_back((int)order.size());
     h->n_cells = (int)cx.size();
     h->n_links = (int)order.size();
-    h->n_link_blocks = std::max(1, (h->n_cells + kBlock - 1) / kBlock);  // >= 1 so that forces are always written
+    // one block (looping over its cells) while the per-link terms fit its shared memory; >= 1 so that forces are always written
+    h->n_link_blocks = K <= kLinkLocal ? 1 : std::max(1, (h->n_cells + kBlock - 1) / kBlock);
     std::vector<int> obs_off(n_obstacles + 1);
     for (int o = 0; o <= n_obstacles; o++) obs_off[o] = (int)offsets[o];
 
@@ -960,6 +1057,11 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     std::vector<unsigned char> mask(mbytes, 0);
     for (size_t c = 0; c < cx.size(); c++) mask[(size_t)cx[c] * h->lay.pitch + cy[c]] = 1;
     CUDA_TRY(up(&h->d_mask, mask.data(), mbytes));
+    if (!h->is_band && !cx.empty()) {
+        int rc = build_band(h, n_obstacles, offsets, ijq, ibb, use_ibb, *std::min_element(cx.begin(), cx.end()),
+                            *std::max_element(cx.begin(), cx.end()));
+        if (rc) return rc;
+    }
     return LBM_OK;
 }
 
@@ -1025,8 +1127,7 @@ int lbm_set_ramp(lbm_t *h, const double *ret_host, int64_t it0, int64_t n)
 {
     CHECK_H(h);
     if (n < 0 || (n > 0 && !ret_host)) return fail(LBM_E_INVALID, "bad ramp table");
-    if (n == 0) {
-        if (h->ramp_n) invalidate_graphs(h);
+    if (n == 0) {                 // (captured batches carry their ramp mode in their key: nothing to invalidate)
         h->ramp_n = 0;
         return LBM_OK;
     }
@@ -1040,7 +1141,6 @@ int lbm_set_ramp(lbm_t *h, const double *ret_host, int64_t it0, int64_t n)
         CUDA_TRY(cudaMalloc(&h->d_ramp, (size_t)cap * h->esz));
         h->ramp_cap = cap;
     }
-    if (h->ramp_n == 0 || h->ramp_it0 != it0) invalidate_graphs(h);   // captured launches hold &ramp[row - it0]
     if (h->cfg.dtype == LBM_F64) {
         CUDA_TRY(cudaMemcpyAsync(h->d_ramp, ret_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -1070,6 +1170,17 @@ static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, 
         // ... and the lattice is large enough to profit: below two full waves of 8 x 64 tiles at 4
         // blocks per SM the single-update kernel is faster (small lattices are latency bound)
         const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * (int64_t)h->n_sm || h->tb_force;
+        if (h->temporal && big && mode == kFused && h->n_obs > 0 && band_usable(h) && plain >= 2 && h->depth >= 2 &&
+            (h->tb_force || h->cfg.nxl * h->cfg.ny >= (1LL << 24))) {
+            const int d = (int)std::min<int64_t>(plain, h->depth);
+            int64_t rows[4];
+            for (int k = 0; k < d; k++) rows[k] = first_row + (s + k) * row_stride;
+            rc = launch_band_group(h, h->cur, h->cur ^ 1, d, rows, s);
+            if (rc) return rc;
+            h->cur ^= 1;
+            s += d - 1;
+            continue;
+        }
         if (h->temporal && big && mode == kFused && h->n_obs == 0 && plain >= 2 && h->cfg.nxl >= 4) {
             int d = (int)std::min<int64_t>(plain, h->depth);
             // wavefront launches pay off from ~4096^2 cells per slab (measured: 4096^2 93 vs 81 GLUPS for
@@ -1127,11 +1238,13 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     if (graph_ok) {
         lbm_handle::StepGraph *g = nullptr;
         for (auto &e : h->graphs)
-            if (e.n == n_updates && e.first_row == first_row && e.stride == row_stride && e.flags == flags && e.cur0 == h->cur) g = &e;
+            if (e.n == n_updates && e.first_row == first_row && e.stride == row_stride && e.flags == flags && e.cur0 == h->cur &&
+                e.ramp == (h->ramp_n > 0) && (!e.ramp || e.ramp_it0 == h->ramp_it0)) g = &e;
         if (!g) {
             if (h->graphs.size() >= 4) invalidate_graphs(h);
             lbm_handle::StepGraph e;
             e.n = n_updates; e.first_row = first_row; e.stride = row_stride; e.flags = flags; e.cur0 = h->cur;
+            e.ramp = h->ramp_n > 0; e.ramp_it0 = h->ramp_it0;
             const int64_t l0 = h->launches;
             CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
             rc = enqueue_updates(h, n_updates, first_row, row_stride, flags);
@@ -1192,12 +1305,22 @@ int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int
 {
     CHECK_H(h);
     if (h->kind != kHaveF) return fail(LBM_E_STATE, "lbm_stepn_columns needs post-collision populations");
-    if (h->n_obs > 0) return fail(LBM_E_UNSUPPORTED, "multi-update launches do not handle obstacle links");
     if (depth < 2 || depth > 4 || !rows) return fail(LBM_E_INVALID, "depth must be 2, 3 or 4 (with one wall row each)");
     if (xa < 0 || xb > h->cfg.nxl || xb - xa < 2) return fail(LBM_E_INVALID, "bad column range (need at least 2 columns)");
     for (int k = 0; k < depth; k++) {
         int rc = check_row(h, rows[k]);
         if (rc) return rc;
+    }
+    if (h->n_obs > 0) {
+        // bodies: the whole slab in one group -- wavefront launches beside the obstacle band, single updates
+        // with the links inside it; drag/lift sums of the updates go to force slots 0 .. depth-1
+        if (xa != 0 || xb != h->cfg.nxl) return fail(LBM_E_UNSUPPORTED, "multi-update launches with obstacle links cover the whole slab");
+        if (!band_usable(h)) return fail(LBM_E_UNSUPPORTED, "no obstacle band on this slab (links next to a slab interface, or peer halos attached)");
+        int rc = ensure_forces(h, depth);
+        if (rc) return rc;
+        rc = launch_band_group(h, h->cur, h->cur ^ 1, depth, rows, 0);
+        if (!rc) { h->force_n = depth; h->force_skip0 = false; }
+        return rc;
     }
     return launch_stepw(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, depth, rows);
 }
@@ -1417,6 +1540,8 @@ int lbm_probe_line(lbm_t *h, int32_t axis, int64_t index, int64_t row, void *out
     }
     dim3 grid((unsigned)((n + kBlock - 1) / kBlock)), block(kBlock);
     const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    rc = peer_wait(h);               // slab runs: the edge cells pull from halo columns the neighbours fill
+    if (rc) return rc;
     if (h->cfg.dtype == LBM_F64) {
         StepParams<double> p; LinkParams lp;
         fill_params<double>(h, p, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, row, 0);
@@ -1447,6 +1572,9 @@ int lbm_peer_export(lbm_t *h, lbm_peer_info *out)
     if (!h->d_flags) {
         CUDA_TRY(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned int)));
         CUDA_TRY(cudaMemset(h->d_flags, 0, 4 * sizeof(unsigned int)));
+        CUDA_TRY(cudaHostAlloc((void **)&h->h_err, sizeof(unsigned int), cudaHostAllocMapped));
+        *h->h_err = 0;
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&h->d_err, h->h_err, 0));
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     memset(out, 0, sizeof *out);

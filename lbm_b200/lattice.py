@@ -471,6 +471,30 @@ class lattice:
         self._cache = {}
         return forces
 
+    def batch_updates_ramp(self, base_row, scales):
+        """batch_updates for wall rows of the form  velocity entries of base_row x scales[k]  (the apps' inlet
+        ramp): the base row is uploaded once, a batch costs 8 bytes of host input per update (lbm_set_ramp)."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "batch_updates() must follow set_bc")
+        self._need_all_bcs()
+        self._push_links()
+        h = self._handle()
+        base_row = np.ascontiguousarray(base_row, dtype=np.float64).reshape(-1)
+        scales = np.ascontiguousarray(scales, dtype=np.float64).reshape(-1)
+        n = scales.size
+        C.check(self._L.lbm_set_walls(h, 1, self._ptr(base_row)))        # (one row; the per-phase calls reuse the slot)
+        self._row_dev = None
+        C.check(self._L.lbm_set_ramp(h, self._ptr(scales), 0, n))
+        C.check(self._L.lbm_step(h, n, 0, 1, C.LBM_STEP_MACRO_LAST))
+        nobs = max(len(self._link_obstacles), 1)
+        forces = np.zeros((n, nobs, 2))
+        C.check(self._L.lbm_get_forces(h, 0, n, self._ptr(forces)))      # waits for the batch: `scales` may go
+        C.check(self._L.lbm_set_ramp(h, None, 0, 0))                     # back to plain rows for the per-phase calls
+        self.updates += n
+        self._state = "macro_done"
+        self._cache = {}
+        return forces
+
     def forces_now(self):
         """[n_obs, 2] momentum-exchange sums of the current post-collision array."""
         self._push_links()

@@ -17,9 +17,73 @@ the updates stored.  What the app sees is identical to the per-phase loop:
 
 The reference's own run() also works with lbm_b200.lattice.lattice (one update per iteration).
 """
+import math
 import time
 
 import numpy as np
+
+
+class InletModel:
+    """Closed form of what app.set_inlets(lattice, it) leaves in the wall-profile arrays, for apps whose inlets are
+    a fixed profile times the ramp of the reference apps,
+
+        velocity entries(it) = fl( s(it) * B ),   s(it) = fl( ret(it) * u_lbm ),   ret(it) = 1 - exp(-it^2 / (2 sigma^2))
+
+    (cavity.py:70-73: u_top = u_lbm*ret, B = 1 on the lid; turek.py:99-104, poiseuille.py, array.py, step.py:
+    u_left = ret*u_lbm*poiseuille(pt), B = the app's own poiseuille() profile).  The model is only used after it
+    has reproduced the app's own set_inlets BIT FOR BIT on a set of probe iterations, and run() re-checks it against
+    the app at the end of every batch; an app that does not fit keeps the per-iteration path.  With a model a
+    batch of updates needs one scalar per iteration from the host (lbm_set_ramp) instead of one call of the app's
+    Python set_inlets and one wall row per iteration."""
+
+    PROBES = (0, 1, 2, 3, 10, 97, 1000, 54321, 10 ** 9)
+
+    def __init__(self, base, sigma, u_lbm, nvel):
+        self.base, self.sigma, self.u_lbm, self.nvel = base, float(sigma), float(u_lbm), nvel
+
+    def scale(self, it):
+        return (1.0 - math.exp(-it ** 2 / (2.0 * self.sigma ** 2))) * self.u_lbm
+
+    def scales(self, its):
+        # (scalar libm calls, like the apps': a vectorised exp may differ in the last bit; ~0.3 us per iteration)
+        return np.array([self.scale(int(it)) for it in its], dtype=np.float64)
+
+    def row(self, it):
+        r = self.base.copy()
+        r[:self.nvel] = self.scale(it) * self.base[:self.nvel]
+        return r
+
+    @classmethod
+    def detect(cls, lattice, app):
+        sigma, u_lbm = getattr(app, "sigma", None), getattr(app, "u_lbm", None)
+        if not sigma or u_lbm is None:
+            return None
+        nx, ny = lattice.nx, lattice.ny
+        nvel = 4 * ny + 4 * nx
+
+        def actual(it):
+            app.set_inlets(lattice, it)
+            return lattice.snapshot_walls()
+        try:
+            full = actual(cls.PROBES[-1])                 # ret == 1.0 exactly
+            candidates = []
+            b = full.copy()
+            b[:nvel] = (full[:nvel] != 0.0).astype(np.float64)      # constant profile (cavity lid)
+            candidates.append(b)
+            if hasattr(app, "poiseuille"):                # channel apps: the app's own inlet profile on the left wall
+                b = full.copy()
+                b[:nvel] = 0.0
+                for j in range(ny):
+                    p = np.asarray(app.poiseuille(lattice.get_coords(0, j)), dtype=np.float64)
+                    b[j], b[ny + j] = p[0], p[1]
+                candidates.append(b)
+            for base in candidates:
+                m = cls(base, sigma, u_lbm, nvel)
+                if all(np.array_equal(m.row(it), actual(it)) for it in cls.PROBES):
+                    return m
+        except Exception:
+            return None
+        return None
 
 
 def _tail_of_iteration(lattice, app, it):
@@ -32,8 +96,9 @@ def _tail_of_iteration(lattice, app, it):
     return app.check_stop(it)
 
 
-def run(lattice, app, batch=512, quiet=False):
+def run(lattice, app, batch=512, quiet=False, inlet_model=True):
     app.initialize(lattice)
+    model = InletModel.detect(lattice, app) if inlet_model and hasattr(lattice, "batch_updates_ramp") else None
     start_time = time.time()
     if not quiet:
         print('### Solving')
@@ -58,13 +123,22 @@ def run(lattice, app, batch=512, quiet=False):
         if stop_on_it and hasattr(app, "it_max"):
             n = max(1, min(n, int(app.it_max) - it + 1))
         # wall rows: update `it+k` applies the boundary conditions of iteration it+k-1
-        rows = [lattice._row.copy()]
-        for k in range(n - 1):
-            app.set_inlets(lattice, it + k)
-            rows.append(lattice.snapshot_walls())
+        if model is not None:
+            if not np.array_equal(lattice._row, model.row(it - 1)):
+                raise RuntimeError("inlet model no longer matches app.set_inlets at iteration %d" % (it - 1))
+            scales = model.scales(np.arange(it - 1, it - 1 + n))
+            rows = None
+        else:
+            rows = [lattice._row.copy()]
+            for k in range(n - 1):
+                app.set_inlets(lattice, it + k)
+                rows.append(lattice.snapshot_walls())
         if exact_stop and n > 1:
             lattice.save_state()
-        forces = lattice.batch_updates(np.stack(rows))       # slot k = iteration it+k-1
+        if model is not None:
+            forces = lattice.batch_updates_ramp(model.base, scales)
+        else:
+            forces = lattice.batch_updates(np.stack(rows))   # slot k = iteration it+k-1
         last = it + n - 1
         stopped_at = None
         for k in range(n - 1):                                # replay iterations it .. last-1
@@ -85,7 +159,10 @@ def run(lattice, app, batch=512, quiet=False):
             m = stopped_at - it + 1
             lattice.restore_state()
             lattice._state = "streamed"
-            lattice.batch_updates(np.stack(rows[:m]))
+            if model is not None:
+                lattice.batch_updates_ramp(model.base, scales[:m])
+            else:
+                lattice.batch_updates(np.stack(rows[:m]))
             lattice.collision_stream()
             app.set_inlets(lattice, stopped_at)
             app.set_bc(lattice)

@@ -10,7 +10,8 @@ stub).  Every array written here is an output of the reference's own code
 beside it, so the fixtures can be replayed anywhere (the GPU box has no
 reference).  Files:
 
-  links_*.npz    obstacle link lists + IBB distances + polygons
+  links_*.npz    obstacle link lists + IBB distances + polygons (written to lbm_b200/data/: the restated
+                 BASELINE cases of lbm_b200/cases.py load them)
                  (lattice.add_obstacle, lattice.py:290-375)
   phases.npz     one call of every nb_* kernel / lattice.macro on seeded inputs
   run_*.npz      free-running driver loops (run.py:24-54 order): final g, g_up,
@@ -64,7 +65,7 @@ def links_fixture(ns, name, app):
     off = np.cumsum([0] + [len(b) for b in bnd]).astype(np.int64)
     poff = np.cumsum([0] + [len(p) for p in poly]).astype(np.int64)
     np.savez_compressed(
-        os.path.join(HERE, "links_%s.npz" % name),
+        os.path.join(os.path.dirname(os.path.dirname(HERE)), "lbm_b200", "data", "links_%s.npz" % name),
         boundary=np.concatenate(bnd), ibb=np.concatenate(ibb), offsets=off,
         polygon=np.concatenate(poly), polygon_offsets=poff,
         solid=np.argwhere(lat.lattice > 0).astype(np.int32),

@@ -24,7 +24,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, tau = 536, 100, 0.62
-    z = np.load(os.path.join(ROOT, "tests", "golden", "links_turek100.npz"))
+    z = np.load(os.path.join(ROOT, "lbm_b200", "data", "links_turek100.npz"))
     bnd = z["boundary"].copy()
     shift = nx // 2 - int(round(bnd[:, 0].mean()))          # cylinder centre -> column nx/2 (an interface for 2 and 4 slabs)
     bnd[:, 0] += shift

@@ -20,7 +20,7 @@ class _Obs:
 
 @pytest.mark.parametrize("name,count", [("turek100", 234), ("turek200", 468), ("array", 928)])
 def test_links_identical_to_reference(name, count):
-    z = np.load(os.path.join(GOLDEN, "links_%s.npz" % name))
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), os.pardir, "lbm_b200", "data", "links_%s.npz" % name))
     lat = _Lat()
     for k in ("nx", "ny"):
         setattr(lat, k, int(z[k]))

@@ -125,6 +125,14 @@ class LazyOracleLattice(orc.OracleLattice):
                 self._state = "streamed"             # same BC set for the following update
         return np.array(forces)
 
+    def batch_updates_ramp(self, base_row, scales):
+        """What the library does with a ramp table: velocity entries of the base row x scale, one rounded product."""
+        nvel = 4 * self.ny + 4 * self.nx
+        rows = np.tile(np.asarray(base_row, dtype=np.float64), (len(scales), 1))
+        rows[:, :nvel] = np.asarray(scales)[:, None] * rows[:, :nvel]
+        self.ramp_batches = getattr(self, "ramp_batches", 0) + 1
+        return self.batch_updates(rows)
+
     def save_state(self):
         self._saved = tuple(a.copy() for a in (self.g, self.g_up, self.rho, self.u)) + (self._advanced,)
 
@@ -170,6 +178,7 @@ def test_batched_driver_equals_the_plain_loop(name, batch):
     assert na == nb and na > 50
     if batch > 1:
         assert max(la.batches) > 1                                   # really batched
+        assert getattr(la, "ramp_batches", 0) > 0                    # ... through the inlet model (one scalar per iteration)
         if name == "turek_obs":
             assert getattr(la, "rollbacks", 0) == 1                  # the stop rule fired inside a batch
     if getattr(ca, "forces", None):
@@ -179,3 +188,51 @@ def test_batched_driver_equals_the_plain_loop(name, batch):
         la._advance()
     for k in ("g", "g_up", "rho", "u"):
         assert np.array_equal(getattr(la, k), getattr(lb, k)), k
+
+
+def test_inlet_model_reproduces_the_apps_bit_for_bit():
+    """InletModel (run.py): closed form of app.set_inlets for the restated cases and -- where the reference is
+    checked out -- for the reference's own cavity / turek / poiseuille / array apps: every wall row it predicts
+    equals what the app writes, bitwise, on iterations that are not among the detection probes."""
+    from lbm_b200.run import InletModel
+    apps = [("cases.cavity", cases.Cavity(L_lbm=40)), ("cases.turek", _cases()["turek_it"]()), ("cases.poiseuille", cases.Poiseuille(L_lbm=20))]
+    from oracle import refload
+    if refload.available():
+        import contextlib
+        import io
+        ns = refload.load()
+        with refload.in_scratch(), contextlib.redirect_stdout(io.StringIO()):
+            for name in ("cavity", "poiseuille", "turek", "array"):
+                a = ns.app.app_factory.create(name)
+                if name == "turek":
+                    a.L_lbm = 60
+                    a.compute_lbm_parameters()
+                apps.append(("ref." + name, a))
+    for name, app in apps:
+        lat = LazyOracleLattice(app)
+        m = InletModel.detect(lat, app)
+        assert m is not None, name
+        for it in (4, 5, 77, 500, 2222, 40000):
+            app.set_inlets(lat, it)
+            assert np.array_equal(m.row(it), lat.snapshot_walls()), (name, it)
+        assert np.array_equal(m.scales([4, 77, 2222]), np.array([m.scale(4), m.scale(77), m.scale(2222)]))
+
+
+def test_inlet_model_rejects_an_app_that_does_not_fit():
+    from lbm_b200.run import InletModel
+
+    class Odd(cases.Cavity):
+        def set_inlets(self, lattice, it):
+            super().set_inlets(lattice, it)
+            lattice.u_top[0, :] += 1.0e-3 * np.sin(0.1 * it)          # not profile x ramp
+    app = Odd(L_lbm=24, sigma=20)
+    app.it_max = 60
+    lat = LazyOracleLattice(app)
+    assert InletModel.detect(lat, app) is None
+    cb = Odd(L_lbm=24, sigma=20)
+    cb.it_max = 60
+    lb = orc.OracleLattice(cb)
+    assert run(lat, app, batch=16, quiet=True) == orc.run_loop(lb, cb)
+    assert getattr(lat, "ramp_batches", 0) == 0
+    lat._advance()
+    assert np.array_equal(lat.g, lb.g)
