@@ -248,7 +248,7 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # BASELINE configs 1-4 (the reference's own small cases) on one GPU: device stepping and the batched driver
 # ------------------------------------------------------------------------------------------
-def small_configs(n_dev=4096, n_drv=2048):
+def small_configs(n_dev=4096, n_drv=8192):
     """Per config: device us per update (lbm_step batches, drag/lift of every update stored on the device)
     and us per iteration of a whole run through lbm_b200.run.run with the app's per-iteration observers."""
     import torch
@@ -291,8 +291,10 @@ def small_configs(n_dev=4096, n_drv=2048):
             lat.close()
         out.append(res)
     return {"configs": out, "note": "L2-resident lattices (2.9-15.5 MB): launch/latency bound, '% of HBM roofline' is nominal; "
-                                    "device = CUDA-graph replay of 1024-update batches; driver = lbm_b200.run.run (batched, "
-                                    "per-iteration host callbacks of the app replayed)"}
+                                    "device = CUDA-graph replay of 1024-update batches, drag/lift of every update summed on the device; "
+                                    "driver = whole run of %d iterations through lbm_b200.run.run (batches of 1024 updates, one ramp scalar "
+                                    "per iteration from the host, per-iteration callbacks of the app replayed; includes the one-off graph "
+                                    "capture)" % n_drv}
 
 
 # ------------------------------------------------------------------------------------------

@@ -72,6 +72,9 @@ struct LinkParams {
     int n_links_total;      // links of the caller's whole list (slots), this slab's or not
     int n_obs;
     const int *cell_x, *cell_y, *cell_off;   // [n_cells], [n_cells], [n_cells+1]
+    const int *grp_cell;                     // [n_groups+1] groups of <= kBlock cells with <= kBlock links
+    const int *link_idx;                     // [n_links] x*pitch + y of the link's cell
+    int n_groups;
     const int *link_q;                       // [n_links] direction fluid -> solid
     const int *link_kind;                    // 0 plain BB, 1 IBB p<1/2, 2 IBB p>=1/2
     const int *link_slot;                    // position in the caller's concatenated list
@@ -81,6 +84,7 @@ struct LinkParams {
     double *forces;                          // [n_obs][2] output slot
     unsigned int *done;                      // block completion counter
     int n_link_blocks;
+    int defer;                               // 1: leave the per-link terms in link_f (a slot of link_fs), no reduction here
 };
 
 // ---- population sources ------------------------------------------------------------------
@@ -183,80 +187,23 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
 // ---------------------------------------------------------------------------------------
 // Obstacle links: one thread per distinct boundary cell (the extra blocks of the step kernel)
 // ---------------------------------------------------------------------------------------
-constexpr int kLinkLocal = 1024;     // per-link terms of up to this many links stay in the link block's shared memory
-
-template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
-__device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
+// Fixed-order sum of per-link terms f[2*k], f[2*k+1] over each obstacle's range [obs_off[o], obs_off[o+1]): warp w sums
+// the links a + w*32 + lane + 256 k (strided partial sums, then a shuffle tree), one thread adds the eight warp sums in
+// warp order; one barrier per pass of (up to) kObsPass obstacles.  The same code serves the three places where forces
+// are summed, so they agree bit for bit.  CG: the terms were written by other blocks of this launch (bypass L1).
+template <bool CG>
+__device__ __forceinline__ void reduce_obstacles(const double *f, const int *obs_off, int n_obs, double *out, int nthreads)
 {
-    using A = Ar<T, STRICT>;
-    // Up to kLinkLocal links (every BASELINE config: 234 / 468 / 928) are handled by ONE block that keeps the
-    // per-link momentum-exchange terms in shared memory and reduces them after a block barrier: no fence,
-    // atomic and second trip through L2 on the critical path of the (latency-bound) small lattices.
-    __shared__ double sf[2 * kLinkLocal];
-    const bool local = lp.n_link_blocks == 1 && lp.n_links_total <= kLinkLocal;
-    if (local) {
-        for (int k = threadIdx.x; k < 2 * lp.n_links_total; k += nthreads) sf[k] = 0.0;   // (links of other slabs stay 0)
-        __syncthreads();
-    }
-    for (int c = block * nthreads + threadIdx.x; c < lp.n_cells; c += lp.n_link_blocks * nthreads) {
-        const int x = lp.cell_x[c], y = lp.cell_y[c];
-        const int idx = x * p.pitch + y;
-        T G[9];
-        if (!FORCE_ONLY) GlobalSource<T>{p}(x, y, G);
-        const T *coef = static_cast<const T *>(lp.link_c);
-        for (int l = lp.cell_off[c]; l < lp.cell_off[c + 1]; l++) {
-            const int q = lp.link_q[l], qb = opp(q), kind = lp.link_kind[l];
-            const int o1 = kCx[qb] * p.pitch + kCy[qb];            // (im, jm) = (i, j) + c_qbar
-            const T *Fq = p.ctr[q] + idx, *Fb = p.ctr[qb] + idx;
-            const T a = __ldg(Fq);
-            const T c0 = coef[3 * l], c1 = coef[3 * l + 1], c2 = coef[3 * l + 2];
-            T val;
-            if (kind == 1)        // nb.py:98-100
-                val = A::sub(A::add(A::mul(c0, a), A::mul(c1, __ldg(Fq + o1))), A::mul(c2, __ldg(Fq + 2 * o1)));
-            else if (kind == 2)   // nb.py:102-104
-                val = A::add(A::add(A::mul(c0, a), A::mul(c1, __ldg(Fb))), A::mul(c2, __ldg(Fb + o1)));
-            else                  // nb.py:117
-                val = a;
-            if (!FORCE_ONLY) {
-#pragma unroll
-                for (int k = 1; k < 9; k++)
-                    if (k == qb) G[k] = val;
-            }
-            // nb.py:64-67: (g_up_q + g_qbar) c_q   (deviation storage: both carry -w_q; the constant
-            // sum_links 2 w_q c_q is added once, in double, on the host)
-            const T g0 = A::add(a, val);
-            const int s = lp.link_slot[l];
-            double *f = local ? sf : lp.link_f;
-            f[2 * s] = (double)A::mul(g0, T(kCx[q]));
-            f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
-        }
-        if (!FORCE_ONLY) finish_cell<T, STRICT, MODE>(p, x, y, G);
-    }
-    // Fixed-order reduction of the per-link terms, per obstacle -- by this block if it is the only one, else by the
-    // last block to finish.  Warp w sums the links a + w*32 + lane + 256 k of the obstacle's range [a, b) (strided
-    // partial sums, then a shuffle tree), thread 0 adds the eight warp sums in warp order: no dependence on
-    // block scheduling, one barrier per pass of (up to) kObsPass obstacles instead of nine per obstacle.
     constexpr int kObsPass = 16;
-    __shared__ bool last;
     __shared__ double red[kObsPass][kBlock / 32][2];
-    if (!local) {
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
-        __syncthreads();
-        if (!last) return;
-        __threadfence();
-    } else {
-        __syncthreads();
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
-    for (int o0 = 0; o0 < lp.n_obs; o0 += kObsPass) {
-        const int no = min(kObsPass, lp.n_obs - o0);
+    for (int o0 = 0; o0 < n_obs; o0 += kObsPass) {
+        const int no = min(kObsPass, n_obs - o0);
         for (int o = 0; o < no; o++) {
             double fx = 0.0, fy = 0.0;
-            for (int k = lp.obs_off[o0 + o] + threadIdx.x; k < lp.obs_off[o0 + o + 1]; k += nthreads) {
-                fx += local ? sf[2 * k] : __ldcg(lp.link_f + 2 * k);
-                fy += local ? sf[2 * k + 1] : __ldcg(lp.link_f + 2 * k + 1);
+            for (int k = obs_off[o0 + o] + threadIdx.x; k < obs_off[o0 + o + 1]; k += nthreads) {
+                fx += CG ? __ldcg(f + 2 * k) : f[2 * k];
+                fy += CG ? __ldcg(f + 2 * k + 1) : f[2 * k + 1];
             }
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) {
@@ -268,13 +215,111 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
         __syncthreads();
         if (threadIdx.x < 2 * no) {
             const int o = threadIdx.x >> 1, c = threadIdx.x & 1;
-            double f = red[o][0][c];
-            for (int w = 1; w < nwarps; w++) f += red[o][w][c];
-            lp.forces[2 * (o0 + o) + c] = f;
+            double v = red[o][0][c];
+            for (int w = 1; w < nwarps; w++) v += red[o][w][c];
+            out[2 * (o0 + o) + c] = v;
         }
         __syncthreads();
     }
-    if (!local && threadIdx.x == 0) *lp.done = 0;
+}
+
+constexpr int kLinkLocal = 1024;     // per-link terms of up to this many links stay in the link block's shared memory
+
+template <typename T, bool STRICT, int MODE, bool FORCE_ONLY>
+__device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int block, int nthreads)
+{
+    using A = Ar<T, STRICT>;
+    // Up to kLinkLocal links (every BASELINE config: 234 / 468 / 928) can be handled by ONE block that keeps the
+    // per-link momentum-exchange terms in shared memory and reduces them after a block barrier: no fence,
+    // atomic and second trip through L2 (the immediate sums of lbm_forces_now / lbm_apply_bc).
+    __shared__ double sf[2 * kLinkLocal];
+    __shared__ T sval[kBlock];           // bounced-back population of link l0 + i of the current group
+    const bool local = !lp.defer && lp.n_link_blocks == 1 && lp.n_links_total <= kLinkLocal;
+    if (local) {
+        for (int k = threadIdx.x; k < 2 * lp.n_links_total; k += nthreads) sf[k] = 0.0;   // (links of other slabs stay 0)
+        __syncthreads();
+    }
+    // The boundary cells come in GROUPS of at most kBlock cells and kBlock links (lp.grp_cell, built by the host).  Two
+    // phases per group, so that the dependent loads of a cell with eight links do not queue up behind each other
+    // (these lattices are latency bound): one thread per LINK evaluates the (interpolated) bounce-back value and the
+    // momentum-exchange term; after a barrier one thread per CELL puts the values into its pulled populations and
+    // finishes the cell (walls, collision, store).
+    for (int g = block; g < lp.n_groups; g += lp.n_link_blocks) {
+        const int c0 = lp.grp_cell[g], c1 = lp.grp_cell[g + 1];
+        const int l0 = lp.cell_off[c0], l1 = lp.cell_off[c1];
+        const int c = c0 + threadIdx.x, l = l0 + threadIdx.x;
+        int x = 0, y = 0;
+        T G[9];
+        if (!FORCE_ONLY && c < c1) {
+            x = lp.cell_x[c]; y = lp.cell_y[c];
+            GlobalSource<T>{p}(x, y, G);
+        }
+        if (l < l1) {
+            const int q = lp.link_q[l], qb = opp(q), kind = lp.link_kind[l], idx = lp.link_idx[l];
+            const T *coef = static_cast<const T *>(lp.link_c) + 3 * l;
+            const int o1 = kCx[qb] * p.pitch + kCy[qb];            // (im, jm) = (i, j) + c_qbar
+            const T *Fq = p.ctr[q] + idx, *Fb = p.ctr[qb] + idx;
+            const T a = __ldg(Fq);
+            const T c0f = coef[0], c1f = coef[1], c2f = coef[2];
+            T val;
+            if (kind == 1)        // nb.py:98-100
+                val = A::sub(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fq + o1))), A::mul(c2f, __ldg(Fq + 2 * o1)));
+            else if (kind == 2)   // nb.py:102-104
+                val = A::add(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fb))), A::mul(c2f, __ldg(Fb + o1)));
+            else                  // nb.py:117
+                val = a;
+            sval[threadIdx.x] = val;
+            // nb.py:64-67: (g_up_q + g_qbar) c_q   (deviation storage: both carry -w_q; the constant
+            // sum_links 2 w_q c_q is added once, in double, on the host)
+            const T g0 = A::add(a, val);
+            const int s = lp.link_slot[l];
+            double *f = local ? sf : lp.link_f;
+            f[2 * s] = (double)A::mul(g0, T(kCx[q]));
+            f[2 * s + 1] = (double)A::mul(g0, T(kCy[q]));
+        }
+        if (!FORCE_ONLY) {
+            __syncthreads();
+            if (c < c1) {
+                for (int k = lp.cell_off[c]; k < lp.cell_off[c + 1]; k++) {     // later links of a cell overwrite earlier ones
+                    const int qb = opp(lp.link_q[k]);
+                    const T v = sval[k - l0];
+#pragma unroll
+                    for (int m = 1; m < 9; m++)
+                        if (m == qb) G[m] = v;
+                }
+                finish_cell<T, STRICT, MODE>(p, x, y, G);
+            }
+            __syncthreads();
+        }
+    }
+    if (lp.defer) return;       // the terms of this update stay in their slot of link_fs: force_reduce_kernel sums them later
+    // Reduction of the per-link terms, per obstacle -- by this block if it is the only one, else by the last block to
+    // finish (no dependence on block scheduling).
+    __shared__ bool last;
+    if (!local) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(lp.done, 1u) == (unsigned)lp.n_link_blocks - 1;
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+        reduce_obstacles<true>(lp.link_f, lp.obs_off, lp.n_obs, lp.forces, nthreads);
+        if (threadIdx.x == 0) *lp.done = 0;
+    } else {
+        __syncthreads();
+        reduce_obstacles<false>(sf, lp.obs_off, lp.n_obs, lp.forces, nthreads);
+    }
+}
+
+// The per-link terms of update slots slot0 + blockIdx.x (written by the link blocks of lbm_step's launches) summed per
+// obstacle, one block per slot: the reduction is off the critical path of the updates, which matters on the small,
+// latency-bound lattices of the reference's own cases (a Turek update took 8.9 us with the sums inside, 2.6 us are
+// the bulk alone).
+__global__ void __launch_bounds__(kBlock)
+force_reduce_kernel(const double *link_fs, int n_links_total, const int *obs_off, int n_obs, double *forces, int slot0)
+{
+    const size_t slot = (size_t)slot0 + blockIdx.x;
+    reduce_obstacles<false>(link_fs + slot * n_links_total * 2, obs_off, n_obs, forces + slot * n_obs * 2, kBlock);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -104,9 +104,15 @@ struct lbm_handle {
     // links
     int n_obs = 0, n_cells = 0, n_links = 0, n_links_total = 0, n_link_blocks = 0;
     int *d_cell_x = nullptr, *d_cell_y = nullptr, *d_cell_off = nullptr, *d_link_q = nullptr,
-        *d_link_kind = nullptr, *d_link_slot = nullptr, *d_obs_off = nullptr;
+        *d_link_kind = nullptr, *d_link_slot = nullptr, *d_obs_off = nullptr, *d_grp_cell = nullptr, *d_link_idx = nullptr;
+    int n_groups = 0;
     void *d_link_c = nullptr;
     double *d_link_f = nullptr;
+    // deferred force sums (lbm_step batches): per-link terms of every update slot [force_cap][n_links_total][2]; the slots
+    // in [force_dirty_lo, force_dirty_hi) have not been summed into d_forces yet (lbm_get_forces does it)
+    double *d_link_fs = nullptr;
+    int64_t link_fs_cap = 0, force_dirty_lo = 0, force_dirty_hi = 0;
+    bool defer_now = false;       // the launches being enqueued leave their sums to force_reduce_kernel
     unsigned int *d_done = nullptr;
     unsigned char *d_mask = nullptr;
     // Obstacle band (multi-update launches on lattices with bodies): a child handle that owns local columns
@@ -221,6 +227,35 @@ static int ensure_forces(lbm_handle *h, int64_t n)
     CUDA_TRY(cudaMalloc(&h->d_forces, (size_t)cap * nobs * 2 * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(h->d_forces, 0, (size_t)cap * nobs * 2 * sizeof(double), h->stream));
     h->force_cap = cap;
+    if (h->d_link_fs) { CUDA_TRY(cudaFree(h->d_link_fs)); h->d_link_fs = nullptr; h->link_fs_cap = 0; }
+    h->force_dirty_lo = h->force_dirty_hi = 0;
+    const size_t fs_bytes = (size_t)cap * (size_t)h->n_links_total * 2 * sizeof(double);
+    if (h->n_links_total > 0 && !h->is_band && fs_bytes <= ((size_t)128 << 20)) {      // (zeros: links of other slabs)
+        CUDA_TRY(cudaMalloc(&h->d_link_fs, fs_bytes));
+        CUDA_TRY(cudaMemsetAsync(h->d_link_fs, 0, fs_bytes, h->stream));
+        h->link_fs_cap = cap;
+    }
+    return LBM_OK;
+}
+
+static void mark_forces_dirty(lbm_handle *h, int64_t lo, int64_t hi)
+{
+    if (!h->d_link_fs || hi <= lo) return;
+    if (h->force_dirty_hi <= h->force_dirty_lo) { h->force_dirty_lo = lo; h->force_dirty_hi = hi; }
+    else { h->force_dirty_lo = std::min(h->force_dirty_lo, lo); h->force_dirty_hi = std::max(h->force_dirty_hi, hi); }
+}
+
+static int reduce_dirty_forces(lbm_handle *h)
+{
+    if (!h->d_link_fs || h->force_dirty_hi <= h->force_dirty_lo) return LBM_OK;
+    const int64_t lo = h->force_dirty_lo, hi = std::min(h->force_dirty_hi, h->link_fs_cap);
+    if (hi > lo) {
+        force_reduce_kernel<<<(unsigned)(hi - lo), kBlock, 0, h->stream>>>(h->d_link_fs, h->n_links_total, h->d_obs_off, h->n_obs,
+                                                                            h->d_forces, (int)lo);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    h->force_dirty_lo = h->force_dirty_hi = 0;
     return LBM_OK;
 }
 
@@ -321,9 +356,11 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     lp.n_obs = h->n_obs;
     lp.cell_x = h->d_cell_x; lp.cell_y = h->d_cell_y; lp.cell_off = h->d_cell_off;
     lp.link_q = h->d_link_q; lp.link_kind = h->d_link_kind; lp.link_slot = h->d_link_slot;
+    lp.grp_cell = h->d_grp_cell; lp.link_idx = h->d_link_idx; lp.n_groups = h->n_groups;
     lp.link_c = h->d_link_c;
     lp.obs_off = h->d_obs_off;
-    lp.link_f = h->d_link_f;
+    lp.defer = h->defer_now && h->d_link_fs && slot < h->link_fs_cap ? 1 : 0;
+    lp.link_f = lp.defer ? h->d_link_fs + (size_t)slot * h->n_links_total * 2 : h->d_link_f;
     lp.forces = h->d_forces ? h->d_forces + slot * std::max(h->n_obs, 1) * 2 : nullptr;
     lp.done = h->d_done;
     lp.n_link_blocks = h->n_link_blocks;
@@ -573,7 +610,8 @@ static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int 
     int extra = 0;
     // link blocks ride along only when the whole slab is processed by this launch
     const bool links_here = mode != kCollideOnly && h->n_link_blocks > 0 && xa == 0 && xb == (int)h->cfg.nxl;
-    if (links_here) extra = (h->n_link_blocks + ytiles - 1) / ytiles;
+    if (lp.defer) lp.n_link_blocks = std::max(1, h->n_groups);   // no reduction in the launch: one block per group of cells
+    if (links_here) extra = (lp.n_link_blocks + ytiles - 1) / ytiles;
     else lp.n_link_blocks = 0;
     if (mode != kCollideOnly && h->n_link_blocks > 0 && !links_here)
         return fail(LBM_E_UNSUPPORTED, "column-restricted updates with obstacles are not supported yet");
@@ -665,6 +703,7 @@ static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64
     b->walls = h->walls; b->wall_rows = h->wall_rows; b->wall_cap = 0;
     b->d_ramp = h->d_ramp; b->ramp_n = h->ramp_n; b->ramp_it0 = h->ramp_it0; b->ramp_cap = 0;
     b->d_forces = h->d_forces; b->force_cap = h->force_cap;
+    b->d_link_fs = h->d_link_fs; b->link_fs_cap = h->link_fs_cap; b->defer_now = h->defer_now;
     b->cfg.right_wall = h->cfg.right_wall;
     b->stream = h->stream;
     // 1. the band's columns out of the source buffer
@@ -730,7 +769,10 @@ int lbm_create(const lbm_cfg *cfg, lbm_t **out)
 static void free_links(lbm_handle *h)
 {
     void *ptrs[] = {h->d_cell_x, h->d_cell_y, h->d_cell_off, h->d_link_q, h->d_link_kind, h->d_link_slot,
-                    h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask, h->d_force_now};
+                    h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask, h->d_force_now, h->is_band ? nullptr : h->d_link_fs,
+                    h->d_grp_cell, h->d_link_idx};
+    h->d_grp_cell = h->d_link_idx = nullptr; h->n_groups = 0;
+    h->d_link_fs = nullptr; h->link_fs_cap = 0; h->force_dirty_lo = h->force_dirty_hi = 0;
     h->d_force_now = nullptr;
     for (void *p : ptrs) if (p) cudaFree(p);
     h->d_cell_x = h->d_cell_y = h->d_cell_off = h->d_link_q = h->d_link_kind = h->d_link_slot = h->d_obs_off = nullptr;
@@ -743,7 +785,7 @@ static void destroy_band(lbm_handle *h)
     if (!h->band) return;
     lbm_handle *b = h->band;
     h->band = nullptr;
-    b->walls = nullptr; b->d_ramp = nullptr; b->d_forces = nullptr;      // aliases of the parent's tables
+    b->walls = nullptr; b->d_ramp = nullptr; b->d_forces = nullptr; b->d_link_fs = nullptr;   // aliases of the parent's tables
     lbm_destroy(b);
 }
 
@@ -1024,8 +1066,19 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     coff.push_back((int)order.size());
     h->n_cells = (int)cx.size();
     h->n_links = (int)order.size();
-    // one block (looping over its cells) while the per-link terms fit its shared memory; >= 1 so that forces are always written
-    h->n_link_blocks = K <= kLinkLocal ? 1 : std::max(1, (h->n_cells + kBlock - 1) / kBlock);
+    // groups of cells for the link blocks: at most kBlock cells and kBlock links each (a cell has at most 8 links)
+    std::vector<int> grp(1, 0), lidx;
+    for (size_t c = 0, cells = 0, lk = 0; c < cx.size(); c++) {
+        const size_t nl = (size_t)(coff[c + 1] - coff[c]);
+        if (cells + 1 > (size_t)kBlock || lk + nl > (size_t)kBlock) { grp.push_back((int)c); cells = 0; lk = 0; }
+        cells++; lk += nl;
+        for (size_t k = 0; k < nl; k++) lidx.push_back(cx[c] * (int)h->lay.pitch + cy[c]);
+    }
+    grp.push_back((int)cx.size());
+    h->n_groups = (int)grp.size() - 1;
+    // immediate sums: one block (looping over the groups) while the per-link terms fit its shared memory, else one block
+    // per group; >= 1 so that forces are always written
+    h->n_link_blocks = K <= kLinkLocal ? 1 : std::max(1, h->n_groups);
     std::vector<int> obs_off(n_obstacles + 1);
     for (int o = 0; o <= n_obstacles; o++) obs_off[o] = (int)offsets[o];
 
@@ -1041,6 +1094,8 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     CUDA_TRY(up(&h->d_link_kind, lkind.data(), lkind.size() * sizeof(int)));
     CUDA_TRY(up(&h->d_link_slot, lslot.data(), lslot.size() * sizeof(int)));
     CUDA_TRY(up(&h->d_obs_off, obs_off.data(), obs_off.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_grp_cell, grp.data(), grp.size() * sizeof(int)));
+    CUDA_TRY(up(&h->d_link_idx, lidx.data(), lidx.size() * sizeof(int)));
     if (h->cfg.dtype == LBM_F64) {
         CUDA_TRY(up(&h->d_link_c, lc.data(), lc.size() * sizeof(double)));
     } else {
@@ -1227,6 +1282,9 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
         if (row_stride == 0) break;
     }
     h->force_skip0 = h->kind == kHaveG;         // a collide-only first update runs no link blocks: slot 0 stays as it is
+    h->force_dirty_lo = h->force_dirty_hi = 0;  // (sums of an earlier batch that nobody fetched are dropped)
+    h->defer_now = true;                        // the link blocks leave their sums to force_reduce_kernel (lbm_get_forces)
+    struct DeferOff { lbm_handle *h; ~DeferOff() { h->defer_now = false; } } defer_off{h};
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     // Small lattices are launch bound (4 us per update at 200 x 200, profiles/README.md): a batch of
     // updates is captured once into a CUDA graph and replayed (the wall table, force slots and
@@ -1268,6 +1326,7 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     }
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->ev_valid = true;
+    if (h->n_obs > 0) mark_forces_dirty(h, h->force_skip0 ? 1 : 0, n_updates);
     h->force_n = n_updates;
     h->other_has_g = false;
     if (flags & LBM_STEP_MACRO_LAST) h->macro_valid = true;
@@ -1284,8 +1343,13 @@ int lbm_step_columns(lbm_t *h, int64_t xa, int64_t xb, int64_t row, int64_t slot
     if (flags & LBM_STEP_MACRO_LAST) { rc = ensure_macro(h); if (rc) return rc; }
     const int mode = h->kind == kHaveG ? kCollideOnly : kFused;
     if (mode == kFused) { rc = check_row(h, row); if (rc) return rc; }
+    h->defer_now = true;
     rc = launch_step(h, mode, h->cur, h->cur ^ 1, (int)xa, (int)xb, row, slot, (flags & LBM_STEP_MACRO_LAST) != 0);
-    if (!rc && mode == kFused && xa == 0 && xb == h->cfg.nxl) h->force_n = std::max<int64_t>(h->force_n, slot + 1);   // link blocks rode along
+    h->defer_now = false;
+    if (!rc && mode == kFused && xa == 0 && xb == h->cfg.nxl) {       // link blocks rode along
+        h->force_n = std::max<int64_t>(h->force_n, slot + 1);
+        if (h->n_obs > 0 && slot < h->link_fs_cap) mark_forces_dirty(h, slot, slot + 1);
+    }
     return rc;
 }
 
@@ -1318,8 +1382,11 @@ int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int
         if (!band_usable(h)) return fail(LBM_E_UNSUPPORTED, "no obstacle band on this slab (links next to a slab interface, or peer halos attached)");
         int rc = ensure_forces(h, depth);
         if (rc) return rc;
+        h->force_dirty_lo = h->force_dirty_hi = 0;
+        h->defer_now = true;
         rc = launch_band_group(h, h->cur, h->cur ^ 1, depth, rows, 0);
-        if (!rc) { h->force_n = depth; h->force_skip0 = false; }
+        h->defer_now = false;
+        if (!rc) { h->force_n = depth; h->force_skip0 = false; mark_forces_dirty(h, 0, depth); }
         return rc;
     }
     return launch_stepw(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, depth, rows);
@@ -1397,6 +1464,7 @@ int lbm_apply_bc(lbm_t *h, int64_t row)
     h->other_has_g = true;
     h->force_n = 1;
     h->force_skip0 = false;
+    h->force_dirty_lo = h->force_dirty_hi = 0;     // slot 0 now holds this call's sums
     return LBM_OK;
 }
 
@@ -1406,6 +1474,7 @@ int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
     if (!out || first < 0 || n < 0 || first + n > h->force_n) return fail(LBM_E_INVALID, "force slots [%lld, %lld) not available (%lld written)", (long long)first, (long long)(first + n), (long long)h->force_n);
     const int nobs = std::max(h->n_obs, 1);
     if (n == 0) return LBM_OK;
+    { int rc = reduce_dirty_forces(h); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(out, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (!h->force_const.empty())

@@ -240,9 +240,9 @@ def _channel_run(case, nx, ny, n, mode, links, depth=4, stepn=False):
         forces = np.concatenate(f)
     else:
         s.step(n, 1, 1)
-        forces = s.forces(0, n)
-    launches = s.launches - l0
-    out = (s.populations("post_collision"), forces, launches, s.checksum())
+        launches = s.launches - l0
+        forces = s.forces(0, n)                 # (+ one force_reduce_kernel launch)
+    out = (s.populations("post_collision"), forces, launches if not stepn else 0, s.checksum())
     s.close()
     return out
 
