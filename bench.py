@@ -290,7 +290,7 @@ def small_configs(n_dev=4096, n_drv=8192):
                    "driver_us_per_iteration": t_run / n * 1e6, "driver_mlups": c.nx * c.ny * n / t_run / 1e6}
             lat.close()
         out.append(res)
-    return {"configs": out, "note": "L2-resident lattices (2.9-15.5 MB): launch/latency bound, '% of HBM roofline' is nominal; "
+    return {"configs": out, "note": "L2-resident lattices (2.9-15.5 MB): launch/latency bound, a percentage of the HBM roofline is nominal there; "
                                     "device = CUDA-graph replay of 1024-update batches, drag/lift of every update summed on the device; "
                                     "driver = whole run of %d iterations through lbm_b200.run.run (batches of 1024 updates, one ramp scalar "
                                     "per iteration from the host, per-iteration callbacks of the app replayed; includes the one-off graph "

@@ -30,6 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(C.LbmCfg) == 4 * 8 + 2 * 8 + 4 * 4
     assert ctypes.sizeof(C.LbmLayout) == 6 * 8
+    assert ctypes.sizeof(C.LbmPeerInfo) == 3 * 64 + 3 * 8 + 8 * 8      # lbm_peer_info
 
 
 def test_null_arguments_are_rejected_without_a_device():
