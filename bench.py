@@ -394,6 +394,9 @@ def gpu_arm(args):
     # result (the two centre lines of rho,u that cavity.line_fields reads).
     xmid, ymid = nx // 2, ny // 2
     owns_mid = s.x0 <= xmid < s.x0 + s.nxl
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    buf_y = torch.empty((3, s.nxl), dtype=tdt).pin_memory()       # results land in pinned host memory
+    buf_x = torch.empty((3, ny), dtype=tdt).pin_memory()
     barrier()
     t0 = time.perf_counter()
     d2h, done = 0, 0
@@ -401,11 +404,11 @@ def gpu_arm(args):
         m = min(depth, K - done)
         s.s.set_ramp(ramp_host[it:it + m], it)
         s.advance(it, m, depth)
-        line_y = s.probe_line(1, ymid, it + m - 1)             # row y = ny/2, this slab's columns (waits for the launch)
-        d2h = line_y.nbytes
+        line_y = s.probe_line(1, ymid, it + m - 1, out=buf_y)  # row y = ny/2, this slab's columns (waits for the launch)
+        d2h = line_y.numel() * line_y.element_size()
         if owns_mid:
-            line_x = s.probe_line(0, xmid - s.x0, it + m - 1)  # column x = nx/2
-            d2h += line_x.nbytes
+            line_x = s.probe_line(0, xmid - s.x0, it + m - 1, out=buf_x)  # column x = nx/2
+            d2h += line_x.numel() * line_x.element_size()
         it += m
         done += m
     torch.cuda.synchronize(dev)

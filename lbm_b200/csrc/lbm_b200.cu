@@ -600,7 +600,7 @@ static int launch_stepw(lbm_handle *h, int src, int dst, int xa, int xb, int dep
 
 template <typename T, bool STRICT>
 static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int xb, int64_t row,
-                         int64_t slot, bool write_macro)
+                         int64_t slot, bool write_macro, bool with_links = true)
 {
     StepParams<T> p;
     LinkParams lp;
@@ -608,24 +608,27 @@ static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int 
     p.write_macro = write_macro ? 1 : 0;
     const int ytiles = (int)((h->cfg.ny + kBlock - 1) / kBlock);
     int extra = 0;
-    // link blocks ride along only when the whole slab is processed by this launch
-    const bool links_here = mode != kCollideOnly && h->n_link_blocks > 0 && xa == 0 && xb == (int)h->cfg.nxl;
-    if (lp.defer) lp.n_link_blocks = std::max(1, h->n_groups);   // no reduction in the launch: one block per group of cells
-    if (links_here) extra = (lp.n_link_blocks + ytiles - 1) / ytiles;
-    else lp.n_link_blocks = 0;
-    if (mode != kCollideOnly && h->n_link_blocks > 0 && !links_here)
-        return fail(LBM_E_UNSUPPORTED, "column-restricted updates with obstacles are not supported yet");
-    dim3 grid(ytiles, (xb - xa) + extra), block(kBlock);
-    if (grid.y > 65535) {
-        // grid.y is limited to 65535: split wide slabs into several launches
+    // grid.y is limited to 65535: wide slabs are split into launches of 32768 columns; the link blocks (they own the
+    // boundary cells wherever those lie: the bulk threads skip masked cells) ride with the last of them
+    if (xa == 0 && xb == (int)h->cfg.nxl && xb - xa > 32768) {
         for (int a = xa; a < xb; a += 32768) {
             const int b = std::min(xb, a + 32768);
-            if (links_here) return fail(LBM_E_UNSUPPORTED, "obstacles on slabs wider than 65535 columns");
-            int rc = launch_step_t<T, STRICT>(h, mode, src, dst, a, b, row, slot, write_macro);
+            int rc = launch_step_t<T, STRICT>(h, mode, src, dst, a, b, row, slot, write_macro, b == xb);
             if (rc) return rc;
         }
         return LBM_OK;
     }
+    // link blocks ride along only when the whole slab is processed by this call
+    const bool whole = (xa == 0 && xb == (int)h->cfg.nxl) || (h->cfg.nxl > 32768 && xb == (int)h->cfg.nxl && (xa % 32768) == 0);
+    const bool links_here = mode != kCollideOnly && h->n_link_blocks > 0 && whole && with_links;
+    if (lp.defer) lp.n_link_blocks = std::max(1, h->n_groups);   // no reduction in the launch: one block per group of cells
+    if (links_here) extra = (lp.n_link_blocks + ytiles - 1) / ytiles;
+    else lp.n_link_blocks = 0;
+    const bool part_of_split = h->cfg.nxl > 32768 && (xa % 32768) == 0 && (xb == (int)h->cfg.nxl || xb - xa == 32768);
+    if (mode != kCollideOnly && h->n_link_blocks > 0 && !links_here && !part_of_split)
+        return fail(LBM_E_UNSUPPORTED, "column-restricted updates with obstacles are not supported (the link blocks ride with whole-slab updates)");
+    dim3 grid(ytiles, (xb - xa) + extra), block(kBlock);
+    if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "more than 65535 columns (+ link blocks) in one launch");
     { int rcw = peer_wait(h); if (rcw) return rcw; }
     switch (mode) {
     case kFused: step_kernel<T, STRICT, kFused><<<grid, block, 0, h->stream>>>(p, lp); break;
@@ -952,7 +955,6 @@ int lbm_equilibrium(lbm_t *h, const void *rho_host, const void *u_host, void *g_
 {
     CHECK_H(h);
     if (!rho_host || !u_host || !g_eq_host) return fail(LBM_E_INVALID, "NULL argument");
-    if (h->cfg.nxl > 65535) return fail(LBM_E_UNSUPPORTED, "lbm_equilibrium: slab wider than 65535 columns");
     // scratch: rho/u device fields + a 9-plane pitched buffer
     const size_t cells = (size_t)h->cfg.nxl * h->lay.pitch;
     void *d_rho = nullptr, *d_u = nullptr, *d_g = nullptr;
@@ -962,17 +964,20 @@ int lbm_equilibrium(lbm_t *h, const void *rho_host, const void *u_host, void *g_
     int rc = copy_field_h2d(h, d_rho, (int64_t)cells, rho_host, 1);
     if (!rc) rc = copy_field_h2d(h, d_u, (int64_t)cells, u_host, 2);
     if (!rc) {
-        dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)h->cfg.nxl), block(kBlock);
         const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
         const int pitch = (int)h->lay.pitch, nxl = (int)h->cfg.nxl, ny = (int)h->cfg.ny;
-        if (h->cfg.dtype == LBM_F64) {
-            if (strict) equilibrium_kernel<double, true><<<grid, block, 0, h->stream>>>((double *)d_g, (long long)cells, pitch, nxl, ny, (const double *)d_rho, (const double *)d_u);
-            else equilibrium_kernel<double, false><<<grid, block, 0, h->stream>>>((double *)d_g, (long long)cells, pitch, nxl, ny, (const double *)d_rho, (const double *)d_u);
-        } else {
-            if (strict) equilibrium_kernel<float, true><<<grid, block, 0, h->stream>>>((float *)d_g, (long long)cells, pitch, nxl, ny, (const float *)d_rho, (const float *)d_u);
-            else equilibrium_kernel<float, false><<<grid, block, 0, h->stream>>>((float *)d_g, (long long)cells, pitch, nxl, ny, (const float *)d_rho, (const float *)d_u);
+        for (int a = 0; a < nxl; a += 32768) {      // (grid.y <= 65535)
+            dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)std::min(32768, nxl - a)), block(kBlock);
+            const size_t off = (size_t)a * pitch;       // the kernel indexes u's second plane with nxl * pitch from its base
+            if (h->cfg.dtype == LBM_F64) {
+                if (strict) equilibrium_kernel<double, true><<<grid, block, 0, h->stream>>>((double *)d_g + off, (long long)cells, pitch, nxl, ny, (const double *)d_rho + off, (const double *)d_u + off);
+                else equilibrium_kernel<double, false><<<grid, block, 0, h->stream>>>((double *)d_g + off, (long long)cells, pitch, nxl, ny, (const double *)d_rho + off, (const double *)d_u + off);
+            } else {
+                if (strict) equilibrium_kernel<float, true><<<grid, block, 0, h->stream>>>((float *)d_g + off, (long long)cells, pitch, nxl, ny, (const float *)d_rho + off, (const float *)d_u + off);
+                else equilibrium_kernel<float, false><<<grid, block, 0, h->stream>>>((float *)d_g + off, (long long)cells, pitch, nxl, ny, (const float *)d_rho + off, (const float *)d_u + off);
+            }
+            h->launches++;
         }
-        h->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "equilibrium_kernel: %s", cudaGetErrorString(e));
     }
@@ -1560,7 +1565,6 @@ int lbm_get_speed(lbm_t *h, const unsigned char *solid_host, void *speed_host)
     CHECK_H(h);
     if (!speed_host) return fail(LBM_E_INVALID, "speed_host is NULL");
     if (!h->macro_valid || !h->u) return fail(LBM_E_STATE, "no macroscopic fields stored: run lbm_step with LBM_STEP_MACRO_LAST");
-    if (h->cfg.nxl > 65535) return fail(LBM_E_UNSUPPORTED, "lbm_get_speed: slab wider than 65535 columns");
     const size_t cells = (size_t)h->cfg.nxl * h->lay.pitch;
     void *d_out = nullptr;
     unsigned char *d_solid = nullptr;
@@ -1573,13 +1577,16 @@ int lbm_get_speed(lbm_t *h, const unsigned char *solid_host, void *speed_host)
         if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "lbm_get_speed: %s", cudaGetErrorString(e));
     }
     if (!rc) {
-        dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)h->cfg.nxl), block(kBlock);
-        const int pitch = (int)h->lay.pitch, ny = (int)h->cfg.ny;
-        if (h->cfg.dtype == LBM_F64)
-            speed_kernel<double><<<grid, block, 0, h->stream>>>((const double *)h->u, (const double *)h->u + cells, d_solid, (double *)d_out, pitch, ny);
-        else
-            speed_kernel<float><<<grid, block, 0, h->stream>>>((const float *)h->u, (const float *)h->u + cells, d_solid, (float *)d_out, pitch, ny);
-        h->launches++;
+        const int pitch = (int)h->lay.pitch, ny = (int)h->cfg.ny, nxl = (int)h->cfg.nxl;
+        for (int a = 0; a < nxl; a += 32768) {      // (grid.y <= 65535)
+            dim3 grid((unsigned)((h->cfg.ny + kBlock - 1) / kBlock), (unsigned)std::min(32768, nxl - a)), block(kBlock);
+            const size_t off = (size_t)a * pitch;
+            if (h->cfg.dtype == LBM_F64)
+                speed_kernel<double><<<grid, block, 0, h->stream>>>((const double *)h->u + off, (const double *)h->u + cells + off, d_solid ? d_solid + off : nullptr, (double *)d_out + off, pitch, ny);
+            else
+                speed_kernel<float><<<grid, block, 0, h->stream>>>((const float *)h->u + off, (const float *)h->u + cells + off, d_solid ? d_solid + off : nullptr, (float *)d_out + off, pitch, ny);
+            h->launches++;
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "speed_kernel: %s", cudaGetErrorString(e));
     }

@@ -379,12 +379,12 @@ class SlabSolver:
                 self.update(rows[0], next_depth=nxt)
             k += d
 
-    def probe_line(self, axis, index, row=0):
+    def probe_line(self, axis, index, row=0, out=None):
         """(rho, ux, uy) along this slab's part of a lattice line (Solver.probe_line), after the halos of the
         current array have landed (the cells on the slab edges pull from them)."""
         if self._halo_ready is not None:
             self.compute.wait_event(self._halo_ready)
-        return self.s.probe_line(axis, index, row)
+        return self.s.probe_line(axis, index, row, out)
 
     def finish(self):
         if self._halo_ready is not None:

@@ -243,9 +243,14 @@ class Solver:
         C.check(self._L.lbm_get_speed(self._h, None if m is None else self._p(m), self._p(out)))
         return out
 
-    def probe_line(self, axis, index, row=0):
-        """(rho, ux, uy) along column x=index (axis 0) or row y=index (axis 1)."""
+    def probe_line(self, axis, index, row=0, out=None):
+        """(rho, ux, uy) along column x=index (axis 0) or row y=index (axis 1).  out: optional pinned torch
+        tensor of shape (3, n) to receive the line (a direct DMA instead of a staged copy)."""
         n = self.ny if axis == 0 else self.nxl
+        if out is not None:
+            assert tuple(out.shape) == (3, n) and out.is_contiguous()
+            C.check(self._L.lbm_probe_line(self._h, axis, index, row, C.c_vp(out.data_ptr())))
+            return out
         out = np.empty((3, n), dtype=self.np_dtype)
         C.check(self._L.lbm_probe_line(self._h, axis, index, row, self._p(out)))
         return out

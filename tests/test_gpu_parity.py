@@ -270,3 +270,29 @@ def test_ramp_rows_outside_the_table_are_rejected():
     s.set_ramp(None)
     s.step(2, 0, 0)                # back to plain rows (one row in the table)
     s.close()
+
+
+def test_slab_wider_than_65535_columns_with_obstacles():
+    """grid.y of a launch is limited to 65535: a 70 000-column channel is updated in launches of 32768 columns,
+    the link blocks ride with the last of them; lbm_equilibrium and the speed field are chunked the same way.
+    STRICT arithmetic against the oracle, bit for bit, with one IBB cylinder in the first and one in the last chunk."""
+    z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+    far = z["boundary"].copy()
+    far[:, 0] += 66000
+    obs = [cases.Obstacle(z["boundary"], z["ibb"]), cases.Obstacle(far, z["ibb"], tag=2)]
+
+    def mk():
+        c = cases.Turek(L_lbm=30, Re_lbm=20.0, sigma=4, links=list(obs))
+        c.nx, c.x_max = 70000, c.x_min + 70000 * (c.y_max - c.y_min) / 30
+        return c
+    cg, co = mk(), mk()
+    lg = gpu_lattice(cg, arith="strict")
+    lo = orc.OracleLattice(co)
+    orc.run_loop(lg, cg, n_iters=7)
+    orc.run_loop(lo, co, n_iters=7)
+    for k in ("g_up", "g", "rho", "u"):
+        assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
+    assert np.max(np.abs(np.array(cg.forces) - np.array(co.forces))) <= 1e-13 * np.max(np.abs(np.array(co.forces)))
+    v = lg.speed()                      # |u| of the last macro(): equals the oracle's off the walls (Zou-He overwrites those)
+    assert np.array_equal(v[1:-1, 1:-1], np.sqrt(lo.u[0] ** 2 + lo.u[1] ** 2)[1:-1, 1:-1])
+    lg.close()
