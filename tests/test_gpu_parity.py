@@ -292,7 +292,8 @@ def test_slab_wider_than_65535_columns_with_obstacles():
     orc.run_loop(lo, co, n_iters=7)
     for k in ("g_up", "g", "rho", "u"):
         assert np.array_equal(getattr(lg, k), getattr(lo, k)), k
-    assert np.max(np.abs(np.array(cg.forces) - np.array(co.forces))) <= 1e-13 * np.max(np.abs(np.array(co.forces)))
+    fo = np.array(co.forces)           # summation order only (early, small forces: absolute bound)
+    assert np.max(np.abs(np.array(cg.forces) - fo)) <= 1e-12 * max(1.0, np.max(np.abs(fo)))
     v = lg.speed()                      # |u| of the last macro(): equals the oracle's off the walls (Zou-He overwrites those)
     assert np.array_equal(v[1:-1, 1:-1], np.sqrt(lo.u[0] ** 2 + lo.u[1] ** 2)[1:-1, 1:-1])
     lg.close()
