@@ -331,6 +331,11 @@ template <typename T, bool STRICT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 step_kernel(const __grid_constant__ StepParams<T> p, const __grid_constant__ LinkParams lp)
 {
+    // Programmatic dependent launch (small, launch-bound lattices: lbm_b200.cu launches with the stream-serialisation
+    // attribute): the NEXT update's grid may be scheduled while this one runs, and this grid does not touch memory
+    // before the previous one has completed and flushed.  Both instructions are no-ops in a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int ncols = p.xb - p.xa;
     if ((int)blockIdx.y >= ncols) {
         if (MODE != kCollideOnly) {

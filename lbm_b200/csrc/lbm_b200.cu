@@ -85,6 +85,7 @@ struct lbm_handle {
     // ramp: per-update scale of the velocity entries of a wall row (lbm_set_ramp); d_one = device scalar 1
     void *d_ramp = nullptr, *d_one = nullptr;
     int64_t ramp_n = 0, ramp_cap = 0, ramp_it0 = 0;
+    bool pdl = true;              // step_kernel: programmatic dependent launch on small lattices
     int wave_l2 = 6;              // stepw_kernel: columns of L2 prefetch ahead of the TMA ring
     int wave_tail = -1;           // stepw_kernel: width of the short chunks at the end of a launch (-1 = auto, 0 = uniform chunks)
     // peer halo exchange (slab runs, one process per GPU; lbm_peer_*)
@@ -630,12 +631,25 @@ static int launch_step_t(lbm_handle *h, int mode, int src, int dst, int xa, int 
     dim3 grid(ytiles, (xb - xa) + extra), block(kBlock);
     if (grid.y > 65535) return fail(LBM_E_UNSUPPORTED, "more than 65535 columns (+ link blocks) in one launch");
     { int rcw = peer_wait(h); if (rcw) return rcw; }
+    // small lattices are launch bound: programmatic dependent launch lets the next update's grid be scheduled while this
+    // one runs (the kernel waits for its predecessor before it reads anything)
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    // (measured, us per update with / without: 536 x 100 2.65 / 2.86, 1073 x 200 4.38 / 4.92, 900 x 200 4.02 / 4.53, but
+    // 200 x 200 -- 200 blocks, less than two per SM -- 2.97 / 2.61: only where a grid is more than one set of resident blocks)
+    const bool pdl = h->pdl && h->cfg.nxl * h->cfg.ny <= (1LL << 21) && (long long)grid.x * grid.y >= 2LL * h->n_sm;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    cudaError_t le;
     switch (mode) {
-    case kFused: step_kernel<T, STRICT, kFused><<<grid, block, 0, h->stream>>>(p, lp); break;
-    case kCollideOnly: step_kernel<T, STRICT, kCollideOnly><<<grid, block, 0, h->stream>>>(p, lp); break;
-    default: step_kernel<T, STRICT, kStreamOnly><<<grid, block, 0, h->stream>>>(p, lp); break;
+    case kFused: le = cudaLaunchKernelEx(&lc, step_kernel<T, STRICT, kFused>, p, lp); break;
+    case kCollideOnly: le = cudaLaunchKernelEx(&lc, step_kernel<T, STRICT, kCollideOnly>, p, lp); break;
+    default: le = cudaLaunchKernelEx(&lc, step_kernel<T, STRICT, kStreamOnly>, p, lp); break;
     }
     h->launches++;
+    CUDA_TRY(le);
     CUDA_TRY(cudaGetLastError());
     return LBM_OK;
 }
@@ -1420,6 +1434,8 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->wave_rows = (int)value;
         h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
+    } else if (!strcmp(key, "pdl")) {
+        h->pdl = value != 0;
     } else if (!strcmp(key, "wave_l2")) {
         if (value < 0 || value > 4096) return fail(LBM_E_INVALID, "wave_l2 must be in [0, 4096]");
         h->wave_l2 = (int)value;

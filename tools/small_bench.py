@@ -11,8 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lbm_b200.solver import Solver
 
 
-def run(nx, ny, temporal, depth, n=1024, reps=4):
+def run(nx, ny, temporal, depth, n=1024, reps=4, pdl=1):
     s = Solver(nx, ny, tau=0.6)
+    s.set_tuning("pdl", pdl)
     s.set_temporal_blocking(temporal)
     s.set_temporal_depth(depth)
     u_top = np.zeros((2, nx)); u_top[0] = 0.1
@@ -35,4 +36,4 @@ if __name__ == "__main__":
     if len(sys.argv) > 2:
         sizes = [(int(sys.argv[1]), int(sys.argv[2]))]
     for nx, ny in sizes:
-        print(nx, ny, "single %.2f us  pairs %.2f us  wave4 %.2f us" % (run(nx, ny, 0, 1), run(nx, ny, -1, 2), run(nx, ny, -1, 4)), flush=True)
+        print(nx, ny, "single %.2f us (no PDL %.2f)  pairs %.2f us" % (run(nx, ny, 0, 1), run(nx, ny, 0, 1, pdl=0), run(nx, ny, -1, 2)), flush=True)
