@@ -51,7 +51,7 @@ import numpy as np  # noqa: E402
 
 BYTES_PER_LUP = {"f64": 144, "f32": 72}      # 9 population reads + 9 writes
 TAU, U_LID = 0.56, 0.1
-FP64_PER_UPDATE = 63                          # FP64 instructions of one fused cell update (d2q9.cuh: collide_fused)
+FP64_PER_UPDATE = 59                          # FP64 instructions of one fused cell update (d2q9.cuh: collide_fused)
 
 
 def lid_ramp(nx, its):

@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblbm_b200.so")
+# (LBM_B200_LIB: development only -- A/B runs of two builds of the library on the same GPU box)
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "liblbm_b200.so")
 _lib = None
 
 LBM_F64, LBM_F32 = 0, 1

@@ -110,9 +110,9 @@ __host__ __device__ constexpr double weight_of(int q) { return q == 0 ? 4.0 / 9.
 template <typename T> struct Coef {
     T one_m_omp, om_p;        // q = 0:      (1-om_p) g0 + om_p geq0                 nb.py:26
     T a_self, a_opp, a_eq;    // q >= 1:     1-(om_p+om_m)/2, (om_p-om_m)/2, (om_p+om_m)/2   nb.py:31-35
-    // FUSED arithmetic (collide_fused): w_q om_p for the three weight classes, 1.5 w_q om_p, 4.5 w_q om_p,
+    // FUSED arithmetic (collide_fused): w_q om_p for the three weight classes, 4.5 w_q om_p,
     // 3 w_q om_m, and the pair coefficients (1 - om_p)/2, (1 - om_m)/2
-    T wp0, wp1, wp5, wh0, wh1, wh5, wq1, wq5, wm1, wm5, cs, cd;
+    T wp0, wp1, wp5, wq1, wq5, wm1, wm5, cs, cd;
 };
 
 // rho = sum_q g_q in index order; u = (c . g) / rho     (lattice.py:181-189, oracle orc_macro)
@@ -153,14 +153,13 @@ __device__ __forceinline__ void macro(const T (&G)[9], T &r, T &ux, T &uy, T &dr
 //     (F_q + F_qbar)/2 = (1 - om_p)/2 (g_q + g_qbar) + om_p eq_s        =: Fs
 //     (F_q - F_qbar)/2 = (1 - om_m)/2 (g_q - g_qbar) + om_m eq_a        =: Fd
 //     F_q = Fs + Fd,   F_qbar = Fs - Fd
-// and, with  m_s = c_q.m = rho s  and  y = 1/rho,
-//     om_p eq_s = om_p w rho + y (4.5 om_p w m_s^2 - 1.5 om_p w m.m),      om_m eq_a = 3 om_m w m_s .
+// and, with  m_s = c_q.m = rho s,  y = 1/rho  and  E = rho - 1.5 (m.m) y,
+//     om_p eq_s = om_p w E + (4.5 om_p w y) m_s^2,      om_m eq_a = 3 om_m w m_s .
 // The pair sums and differences are the ones the moments are built from anyway (rho = g_0 + sum of the
-// four pair sums, m from the four pair differences), so the whole cell costs 63 FP64 instructions
-// (the plain pair form  a_self g_q - a_opp g_qbar + ...  of round 1 took 76), and everything except the
-// last multiply-add by y is independent of the reciprocal: the dependent chain of a cell is
-// 9 loads -> 4 additions -> seed + 3 FMAs -> 1 FMA -> 1 addition  (the multi-update kernels are bound by
-// FP64 issue and dependent-issue latency, profiles/README.md).  Algebraically identical to
+// four pair sums, m from the four pair differences), and E is shared by the three weight classes, so the
+// whole cell costs 59 FP64 instructions (the plain pair form  a_self g_q - a_opp g_qbar + ...  of round 1
+// took 76; keeping everything but one multiply-add independent of the reciprocal costs 63 and measured
+// 1.8 % slower: the kernels are bound by energy and shared-memory traffic rather than by this chain).  Algebraically identical to
 // lattice.py:181-189 + nb.py:10-17 + 25-35; rounding differs at the 1e-16 level like any FMA
 // contraction does.  Deviation storage (f32): om_p (eq_s - w) = om_p w dr + y (...), same form.
 template <typename A, typename T>
@@ -176,14 +175,15 @@ __device__ __forceinline__ void collide_fused(T (&G)[9], const Coef<T> &c, bool 
     const T y = A::rcp(r);
     const T ms[4] = {mx, my, mx + my, my - mx};
     const T m2 = mx * mx + my * my;
-    const T rp0 = sum * c.wp0, rp1 = sum * c.wp1, rp5 = sum * c.wp5;    // om_p w rho  (f32: om_p w dr)
-    const T hp0 = m2 * c.wh0, hp1 = m2 * c.wh1, hp5 = m2 * c.wh5;       // 1.5 om_p w m.m
-    G[0] = (c.one_m_omp * G[0] + rp0) - hp0 * y;
+    // E = rho - 1.5 (m.m) y is shared by all weight classes; b = 4.5 om_p w y
+    const T E = sum - (T(1.5) * m2) * y;
+    const T e0 = E * c.wp0, e1 = E * c.wp1, e5 = E * c.wp5;             // om_p w (rho - 1.5 m.m / rho)   (f32: rho -> dr)
+    const T b1 = c.wq1 * y, b5 = c.wq5 * y;
+    G[0] = c.one_m_omp * G[0] + e0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int q = 2 * k + 1, qb = q + 1;
-        const T K = (k < 2 ? c.wq1 : c.wq5) * (ms[k] * ms[k]) - (k < 2 ? hp1 : hp5);
-        const T Fs = K * y + (c.cs * S[k] + (k < 2 ? rp1 : rp5));
+        const T Fs = (k < 2 ? b1 : b5) * (ms[k] * ms[k]) + (c.cs * S[k] + (k < 2 ? e1 : e5));
         const T Fd = c.cd * D[k] + (k < 2 ? c.wm1 : c.wm5) * ms[k];
         G[q] = Fs + Fd;
         G[qb] = Fs - Fd;

@@ -328,7 +328,6 @@ template <typename T> static void fill_params(const lbm_handle *h, StepParams<T>
     p.coef.a_opp = T(0.5 * (op - om));
     p.coef.a_eq = T(0.5 * (op + om));
     p.coef.wp0 = T(op * 4.0 / 9.0); p.coef.wp1 = T(op / 9.0); p.coef.wp5 = T(op / 36.0);
-    p.coef.wh0 = T(1.5 * op * 4.0 / 9.0); p.coef.wh1 = T(1.5 * op / 9.0); p.coef.wh5 = T(1.5 * op / 36.0);
     p.coef.wq1 = T(4.5 * op / 9.0); p.coef.wq5 = T(4.5 * op / 36.0);
     p.coef.cs = T(0.5 * (1.0 - op)); p.coef.cd = T(0.5 * (1.0 - om));
     p.coef.wm1 = T(3.0 * om / 9.0); p.coef.wm5 = T(3.0 * om / 36.0);

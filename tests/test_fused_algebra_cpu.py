@@ -17,7 +17,6 @@ def collide_fused_numpy(G, om_p, om_m, dev=False):
     one_m_omp = 1.0 - om_p
     cs, cd = 0.5 * (1.0 - om_p), 0.5 * (1.0 - om_m)
     wp = om_p * W                      # om_p w
-    wh = 1.5 * om_p * W                # 1.5 om_p w
     wq = 4.5 * om_p * W                # 4.5 om_p w
     wm = 3.0 * om_m * W                # 3 om_m w
     S = [G[1] + G[2], G[3] + G[4], G[5] + G[6], G[7] + G[8]]
@@ -29,12 +28,12 @@ def collide_fused_numpy(G, om_p, om_m, dev=False):
     y = 1.0 / r
     ms = [mx, my, mx + my, my - mx]
     m2 = mx * mx + my * my
+    E = s - (1.5 * m2) * y
     F = np.empty_like(G)
-    F[0] = (one_m_omp * G[0] + s * wp[0]) - (m2 * wh[0]) * y
+    F[0] = one_m_omp * G[0] + E * wp[0]
     for k in range(4):
         q, qb = 2 * k + 1, 2 * k + 2
-        K = wq[q] * (ms[k] * ms[k]) - m2 * wh[q]
-        Fs = K * y + (cs * S[k] + s * wp[q])
+        Fs = (wq[q] * y) * (ms[k] * ms[k]) + (cs * S[k] + E * wp[q])
         Fd = cd * D[k] + wm[q] * ms[k]
         F[q] = Fs + Fd
         F[qb] = Fs - Fd
