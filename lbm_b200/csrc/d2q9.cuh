@@ -23,6 +23,8 @@ template <typename T, bool STRICT> struct Ar;
 __device__ __forceinline__ double rcp_fast(double b);
 template <> struct Ar<double, true> {
     static constexpr bool strict = true;
+    static __device__ __forceinline__ double mulr(double a, double b) { return __dmul_rn(a, b); }   // (collide_fused is never strict)
+    static __device__ __forceinline__ double fmad(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
@@ -36,6 +38,8 @@ template <> struct Ar<double, true> {
 };
 template <> struct Ar<float, true> {
     static constexpr bool strict = true;
+    static __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fmad(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -70,6 +74,10 @@ __device__ __forceinline__ double mul_rcp(double a, double b, double y /* ~1/b *
 }
 template <> struct Ar<double, false> {
     static constexpr bool strict = false;
+    // explicit forms for collide_fused: which product of  a*b + c*d  gets fused must not be left to the compiler
+    // (it may choose differently in different kernels, and the kernels have to agree bit for bit)
+    static __device__ __forceinline__ double mulr(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fmad(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
@@ -84,6 +92,8 @@ template <> struct Ar<double, false> {
 };
 template <> struct Ar<float, false> {
     static constexpr bool strict = false;
+    static __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fmad(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
@@ -174,23 +184,25 @@ __device__ __forceinline__ void collide_fused(T (&G)[9], const Coef<T> &c, bool 
     const T my = (D[1] + D[2]) + D[3];
     const T y = A::rcp(r);
     const T ms[4] = {mx, my, mx + my, my - mx};
-    const T m2 = mx * mx + my * my;
+    // every multiply-add below is written out (A::fmad = one fused operation, A::mulr = a rounded product): the
+    // compiler must not be the one to decide which product of a sum of two products is fused
+    const T m2 = A::fmad(my, my, A::mulr(mx, mx));
     // E = rho - 1.5 (m.m) y is shared by all weight classes; b = 4.5 om_p w y
-    const T E = sum - (T(1.5) * m2) * y;
-    const T e0 = E * c.wp0, e1 = E * c.wp1, e5 = E * c.wp5;             // om_p w (rho - 1.5 m.m / rho)   (f32: rho -> dr)
-    const T b1 = c.wq1 * y, b5 = c.wq5 * y;
-    G[0] = c.one_m_omp * G[0] + e0;
+    const T E = A::fmad(-A::mulr(T(1.5), m2), y, sum);
+    const T e0 = A::mulr(E, c.wp0), e1 = A::mulr(E, c.wp1), e5 = A::mulr(E, c.wp5);   // om_p w (rho - 1.5 m.m / rho)   (f32: rho -> dr)
+    const T b1 = A::mulr(c.wq1, y), b5 = A::mulr(c.wq5, y);
+    G[0] = A::fmad(c.one_m_omp, G[0], e0);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int q = 2 * k + 1, qb = q + 1;
-        const T Fs = (k < 2 ? b1 : b5) * (ms[k] * ms[k]) + (c.cs * S[k] + (k < 2 ? e1 : e5));
-        const T Fd = c.cd * D[k] + (k < 2 ? c.wm1 : c.wm5) * ms[k];
+        const T Fs = A::fmad(k < 2 ? b1 : b5, A::mulr(ms[k], ms[k]), A::fmad(c.cs, S[k], k < 2 ? e1 : e5));
+        const T Fd = A::fmad(c.cd, D[k], A::mulr(k < 2 ? c.wm1 : c.wm5, ms[k]));
         G[q] = Fs + Fd;
         G[qb] = Fs - Fd;
     }
     if (want_u) {   // lattice.macro's u, only where it is stored
-        ux = mx * y;
-        uy = my * y;
+        ux = A::mulr(mx, y);
+        uy = A::mulr(my, y);
     }
 }
 

@@ -263,9 +263,11 @@ __device__ void link_block(const StepParams<T> &p, const LinkParams &lp, int blo
             const T c0f = coef[0], c1f = coef[1], c2f = coef[2];
             T val;
             if (kind == 1)        // nb.py:98-100
-                val = A::sub(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fq + o1))), A::mul(c2f, __ldg(Fq + 2 * o1)));
+                val = A::strict ? A::sub(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fq + o1))), A::mul(c2f, __ldg(Fq + 2 * o1)))
+                                : A::fmad(-c2f, __ldg(Fq + 2 * o1), A::fmad(c1f, __ldg(Fq + o1), A::mulr(c0f, a)));   // (explicit: see collide_fused)
             else if (kind == 2)   // nb.py:102-104
-                val = A::add(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fb))), A::mul(c2f, __ldg(Fb + o1)));
+                val = A::strict ? A::add(A::add(A::mul(c0f, a), A::mul(c1f, __ldg(Fb))), A::mul(c2f, __ldg(Fb + o1)))
+                                : A::fmad(c2f, __ldg(Fb + o1), A::fmad(c1f, __ldg(Fb), A::mulr(c0f, a)));
             else                  // nb.py:117
                 val = a;
             sval[threadIdx.x] = val;
