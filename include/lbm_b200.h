@@ -184,6 +184,10 @@ int lbm_set_temporal_blocking(lbm_t *h, int32_t enable);
  * lbm_set_temporal_depth bounds the updates per launch that lbm_step chooses by itself
  * (1 = never more than one, 2 = step2_kernel pairs, 3/4 = wavefront launches; default 4). */
 int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int64_t *rows);
+/* 1 if lbm_stepn_columns is available in the handle's present state: no obstacle links, links that all belong to
+ * other slabs, or an obstacle band that stays clear of the slab interfaces (by kHalo columns where peer halos are
+ * attached).  A slab run uses multi-update launches only if every rank says 1 (all ranks issue the same groups). */
+int lbm_can_stepn(const lbm_t *h);
 int lbm_set_temporal_depth(lbm_t *h, int32_t depth);
 /* Launch-shape knobs (measurement, tests): "wave_chunk" = columns swept by one block of a
  * wavefront launch (default: by slab size), "wave_tail" = width of the short chunks that end a

@@ -75,6 +75,7 @@ SIGNATURES = {
     "lbm_step2_columns": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64]),
     "lbm_set_temporal_blocking": (ctypes.c_int, [c_vp, c_i32]),
     "lbm_stepn_columns": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "lbm_can_stepn": (ctypes.c_int, [c_vp]),
     "lbm_set_temporal_depth": (ctypes.c_int, [c_vp, c_i32]),
     "lbm_set_tuning": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "lbm_apply_bc": (ctypes.c_int, [c_vp, c_i64]),

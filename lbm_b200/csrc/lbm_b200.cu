@@ -686,7 +686,9 @@ static int build_band(lbm_handle *h, int32_t n_obstacles, const int64_t *offsets
     if (a < 2) a = 0;                          // (a wavefront launch is at least two columns wide)
     if (b > nxl - 2) b = nxl;
     if ((a == 0 && !wall_l) || (b == nxl && !wall_r)) return LBM_OK;     // band on a slab interface: single updates only
-    if (h->peer[0].attached || h->peer[1].attached) return LBM_OK;
+    // peer halos: the kHalo edge columns must come out of the wavefront launches (their last stage stores them into the
+    // neighbour's halo), so the band has to stay clear of them
+    if ((h->peer[0].attached && a < kHalo) || (h->peer[1].attached && b > nxl - kHalo)) return LBM_OK;
     const int ca = std::max(a - kHalo, 0), cb = std::min(b + kHalo, nxl);
     if (cb - ca < 2 || (a == 0 && b == nxl)) return LBM_OK;
     lbm_cfg c = h->cfg;
@@ -708,7 +710,13 @@ static int build_band(lbm_handle *h, int32_t n_obstacles, const int64_t *offsets
     return LBM_OK;
 }
 
-static bool band_usable(const lbm_handle *h) { return h->band != nullptr && !h->peer[0].attached && !h->peer[1].attached; }
+static bool band_usable(const lbm_handle *h)
+{
+    if (!h->band) return false;
+    return !(h->peer[0].attached && h->band_a < kHalo) && !(h->peer[1].attached && h->band_b > (int)h->cfg.nxl - kHalo);
+}
+// obstacle links are set, but none of them belongs to this slab: the slab is updated like an obstacle-free one
+static bool links_elsewhere(const lbm_handle *h) { return h->n_obs > 0 && h->n_cells == 0; }
 
 // One group of d = 2..4 updates of the whole slab (src -> dst buffer), bodies in the band; force slots slot0 ..
 static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64_t *rows, int64_t slot0)
@@ -1243,7 +1251,7 @@ static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, 
         // ... and the lattice is large enough to profit: below two full waves of 8 x 64 tiles at 4
         // blocks per SM the single-update kernel is faster (small lattices are latency bound)
         const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * (int64_t)h->n_sm || h->tb_force;
-        if (h->temporal && big && mode == kFused && h->n_obs > 0 && band_usable(h) && plain >= 2 && h->depth >= 2 &&
+        if (h->temporal && big && mode == kFused && h->n_obs > 0 && !links_elsewhere(h) && band_usable(h) && plain >= 2 && h->depth >= 2 &&
             (h->tb_force || h->cfg.nxl * h->cfg.ny >= (1LL << 24))) {
             const int d = (int)std::min<int64_t>(plain, h->depth);
             int64_t rows[4];
@@ -1254,7 +1262,7 @@ static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, 
             s += d - 1;
             continue;
         }
-        if (h->temporal && big && mode == kFused && h->n_obs == 0 && plain >= 2 && h->cfg.nxl >= 4) {
+        if (h->temporal && big && mode == kFused && (h->n_obs == 0 || links_elsewhere(h)) && plain >= 2 && h->cfg.nxl >= 4) {
             int d = (int)std::min<int64_t>(plain, h->depth);
             // wavefront launches pay off from ~4096^2 cells per slab (measured: 4096^2 93 vs 81 GLUPS for
             // step2_kernel, 4096 x 2048 the other way round); below that pairs of updates
@@ -1393,6 +1401,16 @@ int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int
         int rc = check_row(h, rows[k]);
         if (rc) return rc;
     }
+    if (links_elsewhere(h)) {       // the bodies lie in other slabs: plain launch, zero sums in this slab's force slots
+        if (xa == 0 && xb == h->cfg.nxl) {
+            int rc = ensure_forces(h, depth);
+            if (rc) return rc;
+            h->force_dirty_lo = h->force_dirty_hi = 0;
+            h->force_n = depth; h->force_skip0 = false;
+            mark_forces_dirty(h, 0, depth);
+        }
+        return launch_stepw(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, depth, rows);
+    }
     if (h->n_obs > 0) {
         // bodies: the whole slab in one group -- wavefront launches beside the obstacle band, single updates
         // with the links inside it; drag/lift sums of the updates go to force slots 0 .. depth-1
@@ -1408,6 +1426,12 @@ int lbm_stepn_columns(lbm_t *h, int64_t xa, int64_t xb, int32_t depth, const int
         return rc;
     }
     return launch_stepw(h, h->cur, h->cur ^ 1, (int)xa, (int)xb, depth, rows);
+}
+
+int lbm_can_stepn(const lbm_t *h)
+{
+    if (!h) return 0;
+    return h->n_obs == 0 || links_elsewhere(h) || band_usable(h) ? 1 : 0;
 }
 
 int lbm_set_temporal_depth(lbm_t *h, int32_t depth)

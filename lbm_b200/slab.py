@@ -183,6 +183,7 @@ class SlabSolver:
         self.updates = 0
         self.n_obs = 0
         self._stage = {}
+        self.multi_ok = True             # multi-update launches possible on every rank (see set_links)
         self.overlap_wave = False        # wavefront launches: one launch per slab, then the exchange (measured faster)
 
     def set_links(self, obstacles, use_ibb=True):
@@ -193,6 +194,14 @@ class SlabSolver:
         momentum-exchange sums over the ranks (one small all-reduce)."""
         self.s.set_links(obstacles, use_ibb)
         self.n_obs = len(obstacles) if obstacles else 0
+        # multi-update launches with bodies: every rank must be able to (bodies in other slabs, or an obstacle band clear
+        # of this slab's interfaces), because all ranks issue the same sequence of update groups
+        ok = 1 if self.s.can_stepn() else 0
+        if self.world > 1:
+            t = self.torch.tensor([ok], dtype=self.torch.int32, device=self.s.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            ok = int(t.item())
+        self.multi_ok = bool(ok)
 
     def forces(self, first, n):
         """[n, n_obs, 2] momentum-exchange sums of update slots first..first+n-1, whole domain."""
@@ -366,9 +375,15 @@ class SlabSolver:
         s.flip()
         self.updates += d
 
-    def advance(self, first_row, n, depth, row_stride=1):
-        """n lattice updates starting with wall row first_row, at most `depth` per launch."""
+    def advance(self, first_row, n, depth, row_stride=1, collect_forces=False):
+        """n lattice updates starting with wall row first_row, at most `depth` per launch.  collect_forces: return
+        the momentum-exchange sums [n, n_obs, 2] of the updates (whole domain), fetched group by group."""
         k = 0
+        out = []
+        if self.n_obs and not self.multi_ok:
+            depth = 1                    # bodies on a slab interface: single updates (the link blocks ride along)
+        elif self.n_obs and depth == 2:
+            depth = 1                    # (two-update launches have no obstacle path)
         for d, nxt in launch_plan(n, depth):
             rows = [first_row + (k + j) * row_stride for j in range(d)]
             if d >= 3 or (d == 2 and depth > 2):
@@ -377,7 +392,11 @@ class SlabSolver:
                 self.update2(rows[0], rows[1], next_depth=nxt)
             else:
                 self.update(rows[0], next_depth=nxt)
+            if collect_forces:
+                out.append(self.forces(0, d))
             k += d
+        if collect_forces:
+            return np.concatenate(out) if out else np.zeros((0, max(self.n_obs, 1), 2))
 
     def probe_line(self, axis, index, row=0, out=None):
         """(rho, ux, uy) along this slab's part of a lattice line (Solver.probe_line), after the halos of the

@@ -178,6 +178,10 @@ class Solver:
         r = (C.c_i64 * len(rows))(*[int(x) for x in rows])
         C.check(self._L.lbm_stepn_columns(self._h, xa, xb, len(rows), r))
 
+    def can_stepn(self):
+        """Whether multi-update launches are available in the present state (obstacle band clear of the slab edges)."""
+        return bool(self._L.lbm_can_stepn(self._h))
+
     def set_temporal_depth(self, depth):
         C.check(self._L.lbm_set_temporal_depth(self._h, int(depth)))
 

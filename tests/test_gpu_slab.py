@@ -67,3 +67,15 @@ def test_slab_with_obstacle_across_the_interface(exchange):
     world = _world()
     out = _torchrun(world, 29655, "slab_obs_worker.py", 60, exchange)
     assert out["ok"] and out["pop_equal"] and out["straddles"] and out["max_force_diff"] < 1e-12
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("place", ["interior", "interface"])
+def test_slab_obstacle_band_with_multi_update_groups(exchange, place):
+    """Bodies + four updates per group on slabs: a cylinder inside one slab gets an obstacle band there while the
+    other ranks run plain wavefront launches (multi_ok on every rank); a cylinder ON an interface makes every rank
+    fall back to single updates.  Either way: populations bitwise equal to one GPU, force series to rounding."""
+    world = _world()
+    out = _torchrun(world, 29691, "slab_obs_worker.py", 61, exchange, place, 4)
+    assert out["ok"] and out["pop_equal"] and out["max_force_diff"] < 1e-12
+    assert out["multi_ok"] == (place == "interior")
