@@ -289,12 +289,31 @@ def small_configs(n_dev=4096, n_drv=8192):
                    "device_us_per_update": t_raw / done * 1e6, "device_mlups": c.nx * c.ny * done / t_raw / 1e6,
                    "driver_us_per_iteration": t_run / n * 1e6, "driver_mlups": c.nx * c.ny * n / t_run / 1e6}
             lat.close()
+        # the drop-in mode: the reference's run() phase order (run.py:27-48), one library call per phase from Python
+        c = mk()
+        lat = lattice(c, make_dirs=False)
+        c.initialize(lat)
+        n_pp = 1500
+        for it in range(n_pp + 100):
+            if it == 100:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            c.set_inlets(lat, it)
+            lat.macro()
+            lat.equilibrium()
+            lat.collision_stream()
+            c.set_bc(lat)
+            c.observables(lat, it)
+        torch.cuda.synchronize()
+        res["per_phase_us_per_iteration"] = (time.perf_counter() - t0) / n_pp * 1e6
+        lat.close()
         out.append(res)
     return {"configs": out, "note": "L2-resident lattices (2.9-15.5 MB): launch/latency bound, a percentage of the HBM roofline is nominal there; "
                                     "device = CUDA-graph replay of 1024-update batches, drag/lift of every update summed on the device; "
                                     "driver = whole run of %d iterations through lbm_b200.run.run (batches of 1024 updates, one ramp scalar "
                                     "per iteration from the host, per-iteration callbacks of the app replayed; includes the one-off graph "
-                                    "capture)" % n_drv}
+                                    "capture); per_phase = the reference's own run() loop order on the drop-in lattice class (one fused "
+                                    "update per macro() call, drag/lift fetched every iteration)" % n_drv}
 
 
 # ------------------------------------------------------------------------------------------

@@ -387,8 +387,8 @@ class lattice:
 
     def _push_walls(self):
         if self._row_dev is None or not np.array_equal(self._row, self._row_dev):
+            # (pageable host memory: the copy has left the host buffer when the call returns -- no stream sync)
             C.check(self._L.lbm_set_walls(self._handle(), 1, self._ptr(self._row)))
-            C.check(self._L.lbm_sync(self._handle()))
             self._row_dev = self._row.copy()
 
     def _push_links(self):
