@@ -91,13 +91,19 @@ struct LinkParams {
 // A source hands out the nine populations ARRIVING at cell (x, y): G_q = F_q((x,y) - c_q).
 // Entries with no in-domain source are garbage and are overwritten by the wall code
 // (SURVEY.md section 9.3).
-template <typename T> struct GlobalSource {
+// CG: loads that bypass L1 (ld.global.cg) -- for the resident kernel, where the source was written by other blocks of
+// the SAME launch (an L1 line or a non-coherent load could be stale); everywhere else the read-only path.
+template <bool CG, typename T> __device__ __forceinline__ T load_pop(const T *a) { return CG ? __ldcg(a) : __ldg(a); }
+// shift: elements from the buffer p.pull describes to the buffer actually read (the resident kernel alternates between
+// the two buffers, which have the same layout; 0 -- and folded away -- everywhere else).
+template <typename T, bool CG = false> struct GlobalSource {
     const StepParams<T> &p;
+    long long shift = 0;
     __device__ __forceinline__ void operator()(int x, int y, T (&G)[9]) const
     {
         const int idx = x * p.pitch + y;
 #pragma unroll
-        for (int q = 0; q < 9; q++) G[q] = __ldg(p.pull[q] + idx);
+        for (int q = 0; q < 9; q++) G[q] = load_pop<CG>(p.pull[q] + shift + idx);
     }
 };
 
@@ -155,14 +161,17 @@ __device__ __forceinline__ bool apply_walls(const StepParams<T> &p, const T *wal
 }
 
 // Everything after the populations of a cell are in registers: walls, macro, collision, store.
-template <typename T, bool STRICT, int MODE>
-__device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y, T (&G)[9])
+// (walls / scale: the wall row and ramp factor of this update -- p.walls / p.scale except in the resident kernel;
+// sshift / dshift: see GlobalSource, for the source and the destination buffer)
+template <typename T, bool STRICT, int MODE, bool CG = false>
+__device__ __forceinline__ void finish_cell_w(const StepParams<T> &p, const T *walls, const T *scale, int x, int y, T (&G)[9],
+                                              long long sshift = 0, long long dshift = 0)
 {
     using A = Ar<T, STRICT>;
     const int idx = x * p.pitch + y;
     if (MODE != kCollideOnly) {
         T r, ux, uy;
-        const bool on_wall = apply_walls<A, T>(p, p.walls, p.scale, GlobalSource<T>{p}, x, y, G, r, ux, uy);
+        const bool on_wall = apply_walls<A, T>(p, walls, scale, GlobalSource<T, CG>{p, sshift}, x, y, G, r, ux, uy);
         if (MODE == kStreamOnly) {
             if (on_wall && p.rho_out) {
                 p.rho_out[idx] = r;
@@ -181,7 +190,12 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y
         }
     }
 #pragma unroll
-    for (int q = 0; q < 9; q++) p.dst[q][idx] = G[q];
+    for (int q = 0; q < 9; q++) (p.dst[q] + dshift)[idx] = G[q];
+}
+template <typename T, bool STRICT, int MODE>
+__device__ __forceinline__ void finish_cell(const StepParams<T> &p, int x, int y, T (&G)[9])
+{
+    finish_cell_w<T, STRICT, MODE, false>(p, p.walls, p.scale, x, y, G);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@
 #include "../../include/lbm_b200.h"
 
 #include "kernels.cuh"
+#include "resident.cuh"
 
 // =========================================================================================
 // Host side: handle + C ABI
@@ -141,6 +142,18 @@ struct lbm_handle {
     };
     std::vector<StepGraph> graphs;
     bool use_graph = true;
+    // resident batches on small lattices (stepr_kernel, resident.cuh): block layout and dependency lists, built on first use
+    struct Resident {
+        bool built = false, usable = false;
+        int n_blocks = 0, n_col_blocks = 0;
+        int *d_col_a = nullptr, *d_dep_off = nullptr, *d_dep = nullptr;
+        unsigned int *d_prog = nullptr;
+    } res;
+    bool resident = true;              // lbm_set_tuning("resident", 0) keeps the one-launch-per-update path
+    int resident_blocks = 0;           // blocks per SM (0 = what fits)
+    int resident_flags = 0;
+    int64_t resident_timeout_ms = 4000;
+    std::vector<int> grp_x0, grp_x1;   // first / last column of each link group
     // accounting
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -148,6 +161,13 @@ struct lbm_handle {
 };
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+static void free_resident(lbm_handle *h)
+{
+    void *ptrs[] = {h->res.d_col_a, h->res.d_dep_off, h->res.d_dep, h->res.d_prog};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    h->res = lbm_handle::Resident();
+}
 
 static void invalidate_graphs(lbm_handle *h)
 {
@@ -257,6 +277,16 @@ static int reduce_dirty_forces(lbm_handle *h)
         CUDA_TRY(cudaGetLastError());
     }
     h->force_dirty_lo = h->force_dirty_hi = 0;
+    return LBM_OK;
+}
+
+// Time-out word of the device-side waits (peer flags, resident batches): pinned host memory, mapped
+static int ensure_err(lbm_handle *h)
+{
+    if (h->h_err) return LBM_OK;
+    CUDA_TRY(cudaHostAlloc((void **)&h->h_err, sizeof(unsigned int), cudaHostAllocMapped));
+    *h->h_err = 0;
+    CUDA_TRY(cudaHostGetDevicePointer((void **)&h->d_err, h->h_err, 0));
     return LBM_OK;
 }
 
@@ -753,6 +783,146 @@ static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64
 }
 
 // ---------------------------------------------------------------------------------------
+// Resident batches (stepr_kernel, resident.cuh): block layout and dependency lists of the handle's lattice.
+// Column block i owns columns [i nx / n, (i+1) nx / n), reads one column beyond them; link group g owns the boundary
+// cells in columns [grp_x0, grp_x1] and reads two beyond (interpolated bounce-back).  i depends on j when the columns
+// one of them reads meet the columns the other writes.
+static bool resident_candidate(const lbm_handle *h)
+{
+    return h->resident && h->temporal && !h->tb_force && !h->is_band && h->stream != nullptr && h->cfg.x0 == 0 && h->cfg.nxl == h->cfg.nx &&
+           h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached &&
+           (h->n_obs == 0 || (h->n_cells > 0 && h->n_groups <= 64));
+}
+
+template <typename T, bool STRICT>
+static int build_resident(lbm_handle *h)
+{
+    auto &r = h->res;
+    free_resident(h);
+    r.built = true;
+    int coop = 0, occ = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
+    if (h->resident_blocks >= 3) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stepr_kernel<T, STRICT, 3>, kBlock, 0));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stepr_kernel<T, STRICT, 2>, kBlock, 0));
+    if (h->resident_blocks > 0) occ = std::min(occ, h->resident_blocks);
+    const int ng = h->n_obs > 0 ? h->n_groups : 0;
+    const int max_blocks = occ * h->n_sm;
+    if (!coop || max_blocks - ng < 1) return LBM_OK;                // not usable: the per-update launches stay
+    const int nx = (int)h->cfg.nxl;
+    const int ncb = std::min(nx, max_blocks - ng), nb = ncb + ng;
+    std::vector<int> col_a(ncb + 1);
+    for (int i = 0; i <= ncb; i++) col_a[i] = (int)((int64_t)i * nx / ncb);
+    struct Iv { int w0, w1, r0, r1; };
+    std::vector<Iv> iv(nb);
+    // (a corner cell takes rho and u from its x-neighbour on the horizontal wall, whose pulled populations come from one
+    // column further: the blocks with the first / last lattice column read two columns beyond it)
+    for (int i = 0; i < ncb; i++)
+        iv[i] = {col_a[i], col_a[i + 1] - 1, col_a[i] - (col_a[i + 1] == nx ? 2 : 1), col_a[i + 1] + (col_a[i] == 0 ? 1 : 0)};
+    for (int g = 0; g < ng; g++) iv[ncb + g] = {h->grp_x0[g], h->grp_x1[g], h->grp_x0[g] - 2, h->grp_x1[g] + 2};
+    auto meets = [](int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; };
+    std::vector<int> dep_off(nb + 1, 0), dep;
+    for (int i = 0; i < nb; i++) {
+        for (int j = 0; j < nb; j++)
+            if (j != i && (meets(iv[i].r0, iv[i].r1, iv[j].w0, iv[j].w1) || meets(iv[j].r0, iv[j].r1, iv[i].w0, iv[i].w1)))
+                dep.push_back(j);
+        dep_off[i + 1] = (int)dep.size();
+    }
+    if (dep.empty()) dep.push_back(0);
+    CUDA_TRY(cudaMalloc(&r.d_col_a, col_a.size() * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&r.d_dep_off, dep_off.size() * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&r.d_dep, dep.size() * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&r.d_prog, ((size_t)nb * kProgStride + kProgStride) * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemcpy(r.d_col_a, col_a.data(), col_a.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_dep_off, dep_off.data(), dep_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r.d_dep, dep.data(), dep.size() * sizeof(int), cudaMemcpyHostToDevice));
+    r.n_blocks = nb;
+    r.n_col_blocks = ncb;
+    int rc = ensure_err(h);
+    if (rc) return rc;
+    r.usable = true;
+    return LBM_OK;
+}
+
+// n consecutive fused updates in ONE launch: rows first_row, first_row + row_stride, .., force slots slot0 ..
+template <typename T, bool STRICT>
+static int launch_resident_t(lbm_handle *h, int64_t n, int64_t first_row, int64_t row_stride, int64_t slot0)
+{
+    auto &r = h->res;
+    StepParams<T> pa;
+    LinkParams lp;
+    fill_params<T>(h, pa, lp, h->cur, h->cur ^ 1, 0, (int)h->cfg.nxl, first_row, slot0);
+    ResidentParams<T> rp;
+    const ptrdiff_t delta_b = static_cast<const char *>(h->buf[h->cur ^ 1]) - static_cast<const char *>(h->buf[h->cur]);
+    if (delta_b % (ptrdiff_t)sizeof(T)) return fail(LBM_E_INVALID, "population buffers are not element-aligned to each other");
+    rp.buf_delta = delta_b / (ptrdiff_t)sizeof(T);
+    rp.n_updates = (int)n;
+    rp.n_col_blocks = r.n_col_blocks;
+    rp.col_a = r.d_col_a; rp.dep_off = r.d_dep_off; rp.dep = r.d_dep;
+    rp.prog = r.d_prog;
+    rp.err = h->d_err;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
+    rp.timeout_clk = (long long)h->resident_timeout_ms * std::max(khz, 1000000);
+    rp.walls = static_cast<const T *>(h->walls);
+    rp.row_len = h->row_len; rp.wall_rows = std::max<int64_t>(h->wall_rows, 1);
+    rp.first_row = first_row; rp.row_stride = row_stride;
+    rp.ramp = h->ramp_n > 0 ? static_cast<const T *>(h->d_ramp) - h->ramp_it0 : nullptr;
+    rp.one = static_cast<const T *>(h->d_one);
+    rp.link_fs = h->d_link_fs;
+    rp.fs_stride = (long long)h->n_links_total * 2;
+    rp.slot0 = slot0;
+    rp.flags = h->resident_flags;
+    static long long *dbg = nullptr;
+    if ((rp.flags & 8) && !dbg) cudaMalloc(&dbg, (size_t)2048 * 64 * 4 * sizeof(long long));
+    rp.dbg = dbg;
+    CUDA_TRY(cudaMemsetAsync(r.d_prog, 0, ((size_t)r.n_blocks * kProgStride + kProgStride) * sizeof(unsigned int), h->stream));
+    void *args[] = {&pa, &lp, &rp};
+    const void *fn = h->resident_blocks >= 3 ? (const void *)stepr_kernel<T, STRICT, 3> : (const void *)stepr_kernel<T, STRICT, 2>;
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(r.n_blocks), dim3(kBlock), args, 0, h->stream));
+    h->launches++;
+    if ((rp.flags & 8) && n >= 200) {
+        cudaStreamSynchronize(h->stream);
+        std::vector<long long> hd((size_t)r.n_blocks * 64 * 4);
+        cudaMemcpy(hd.data(), dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (int b : {0, 1, r.n_col_blocks / 2, r.n_col_blocks - 1, r.n_blocks - 1}) {
+            double w = 0, c = 0, p = 0, tot = 0;
+            for (int k = 1; k < 64; k++) {
+                const long long *d = &hd[((size_t)b * 64 + k) * 4], *dp = d - 4;
+                w += d[1] - d[0]; c += d[2] - d[1]; p += d[3] - d[2]; tot += d[0] - dp[0];
+            }
+            fprintf(stderr, "[resident dbg] block %d of %d: wait %.0f compute %.0f publish %.0f | per update %.0f cycles\n", b, r.n_blocks, w / 63, c / 63, p / 63, tot / 63);
+        }
+    }
+    return LBM_OK;
+}
+
+// Whether a run of `n` fused updates starting at force slot `slot0` can go through stepr_kernel (builds the layout on
+// first use).
+static bool resident_usable(lbm_handle *h, int64_t n, int64_t slot0, int *rc)
+{
+    *rc = LBM_OK;
+    if (n < 4 || n > (1 << 30) || !resident_candidate(h)) return false;
+    if (h->n_obs > 0 && (!h->d_link_fs || slot0 + n > h->link_fs_cap)) return false;    // (per-link terms need a slot each)
+    if (!h->res.built) {
+        const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+        if (h->cfg.dtype == LBM_F64) *rc = strict ? build_resident<double, true>(h) : build_resident<double, false>(h);
+        else *rc = strict ? build_resident<float, true>(h) : build_resident<float, false>(h);
+        if (*rc) return false;
+    }
+    return h->res.usable;
+}
+
+static int launch_resident(lbm_handle *h, int64_t n, int64_t first_row, int64_t row_stride, int64_t slot0)
+{
+    const bool strict = h->cfg.arith == LBM_ARITH_STRICT;
+    if (h->cfg.dtype == LBM_F64)
+        return strict ? launch_resident_t<double, true>(h, n, first_row, row_stride, slot0)
+                      : launch_resident_t<double, false>(h, n, first_row, row_stride, slot0);
+    return strict ? launch_resident_t<float, true>(h, n, first_row, row_stride, slot0)
+                  : launch_resident_t<float, false>(h, n, first_row, row_stride, slot0);
+}
+
+// ---------------------------------------------------------------------------------------
 extern "C" {
 
 int lbm_abi_version(void) { return LBM_ABI_VERSION; }
@@ -792,6 +962,8 @@ int lbm_create(const lbm_cfg *cfg, lbm_t **out)
 
 static void free_links(lbm_handle *h)
 {
+    free_resident(h);
+    h->grp_x0.clear(); h->grp_x1.clear();
     void *ptrs[] = {h->d_cell_x, h->d_cell_y, h->d_cell_off, h->d_link_q, h->d_link_kind, h->d_link_slot,
                     h->d_obs_off, h->d_link_c, h->d_link_f, h->d_done, h->d_mask, h->d_force_now, h->is_band ? nullptr : h->d_link_fs,
                     h->d_grp_cell, h->d_link_idx};
@@ -890,8 +1062,12 @@ int lbm_sync(lbm_t *h)
 {
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->h_err && *(volatile unsigned int *)h->h_err)
-        return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", *h->h_err);
+    if (h->h_err && *(volatile unsigned int *)h->h_err) {
+        const unsigned int e = *h->h_err;
+        if (e & 0x80000000u)
+            return fail(LBM_E_STATE, "resident batch (stepr_kernel) timed out waiting for a neighbour block at update %u of the launch", e & 0x7fffffffu);
+        return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", e);
+    }
     return LBM_OK;
 }
 
@@ -1102,6 +1278,10 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     }
     grp.push_back((int)cx.size());
     h->n_groups = (int)grp.size() - 1;
+    for (int g = 0; g < h->n_groups; g++) {        // (cells are sorted by column)
+        h->grp_x0.push_back(cx[grp[g]]);
+        h->grp_x1.push_back(cx[grp[g + 1] - 1]);
+    }
     // immediate sums: one block (looping over the groups) while the per-link terms fit its shared memory, else one block
     // per group; >= 1 so that forces are always written
     h->n_link_blocks = K <= kLinkLocal ? 1 : std::max(1, h->n_groups);
@@ -1251,6 +1431,15 @@ static int enqueue_updates(lbm_handle *h, int64_t n_updates, int64_t first_row, 
         // ... and the lattice is large enough to profit: below two full waves of 8 x 64 tiles at 4
         // blocks per SM the single-update kernel is faster (small lattices are latency bound)
         const bool big = ((h->cfg.nxl + 7) / 8) * ((h->cfg.ny + 63) / 64) >= 2 * 4 * (int64_t)h->n_sm || h->tb_force;
+        // small lattices: the whole run of plain updates in ONE resident launch (stepr_kernel)
+        if (mode == kFused && resident_usable(h, plain, s, &rc)) {
+            rc = launch_resident(h, plain, first_row + s * row_stride, row_stride, s);
+            if (rc) return rc;
+            h->cur ^= (int)(plain & 1);
+            s += plain - 1;
+            continue;
+        }
+        if (rc) return rc;
         if (h->temporal && big && mode == kFused && h->n_obs > 0 && !links_elsewhere(h) && band_usable(h) && plain >= 2 && h->depth >= 2 &&
             (h->tb_force || h->cfg.nxl * h->cfg.ny >= (1LL << 24))) {
             const int d = (int)std::min<int64_t>(plain, h->depth);
@@ -1318,7 +1507,8 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     // (<= 2^19 cells: below the size at which multi-update kernels take over, so that a captured batch
     // consists of step_kernel launches only)
     const bool graph_ok = h->use_graph && h->stream != nullptr && h->kind == kHaveF && n_updates >= 16 &&
-                          h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached;
+                          h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached &&
+                          !resident_candidate(h);   // (a resident batch is one launch already)
     if (graph_ok) {
         lbm_handle::StepGraph *g = nullptr;
         for (auto &e : h->graphs)
@@ -1457,6 +1647,17 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->wave_rows = (int)value;
         h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
+    } else if (!strcmp(key, "resident")) {
+        h->resident = value != 0;
+    } else if (!strcmp(key, "resident_blocks")) {
+        if (value < 0 || value > 32) return fail(LBM_E_INVALID, "resident_blocks must be in [0, 32] (blocks per SM, 0 = what fits)");
+        h->resident_blocks = (int)value;
+        free_resident(h);
+    } else if (!strcmp(key, "resident_flags")) {
+        h->resident_flags = (int)value;
+    } else if (!strcmp(key, "resident_timeout_ms")) {
+        if (value < 1) return fail(LBM_E_INVALID, "resident_timeout_ms must be positive");
+        h->resident_timeout_ms = value;
     } else if (!strcmp(key, "pdl")) {
         h->pdl = value != 0;
     } else if (!strcmp(key, "wave_l2")) {
@@ -1687,10 +1888,8 @@ int lbm_peer_export(lbm_t *h, lbm_peer_info *out)
     if (!h->d_flags) {
         CUDA_TRY(cudaMalloc(&h->d_flags, 4 * sizeof(unsigned int)));
         CUDA_TRY(cudaMemset(h->d_flags, 0, 4 * sizeof(unsigned int)));
-        CUDA_TRY(cudaHostAlloc((void **)&h->h_err, sizeof(unsigned int), cudaHostAllocMapped));
-        *h->h_err = 0;
-        CUDA_TRY(cudaHostGetDevicePointer((void **)&h->d_err, h->h_err, 0));
     }
+    { int rce = ensure_err(h); if (rce) return rce; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     memset(out, 0, sizeof *out);
     static_assert(sizeof(cudaIpcMemHandle_t) <= LBM_IPC_HANDLE_BYTES, "IPC handle size");

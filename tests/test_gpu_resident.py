@@ -1,0 +1,159 @@
+"""GPU: resident batches (stepr_kernel, lbm_b200/csrc/resident.cuh) -- a whole run of updates of a small lattice in ONE
+cooperative launch, the blocks handing over to their neighbours through progress words -- are bit-identical to one
+launch per update: every wall variant, time-dependent wall rows and ramp tables, odd sizes (one column per block,
+several columns per block, columns taller than a block), obstacle links (one and several link groups, IBB and plain
+bounce-back) with the stored drag/lift sums, f32, both register budgets, repeated launches with odd update counts."""
+import os
+
+import numpy as np
+import pytest
+
+from lbm_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+W = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+
+
+def _rows(nx, ny, n, seed, pressure):
+    rng = np.random.default_rng(seed)
+    rows = np.zeros((n, 5 * ny + 4 * nx))
+    yy = np.linspace(0, 1, ny)
+    for k in range(n):
+        a = 1.0 - np.exp(-(k + 1) ** 2 / 18.0)
+        rows[k, 0:ny] = 0.04 * a * 4 * yy * (1 - yy)
+        rows[k, ny:2 * ny] = 0.002 * a * rng.standard_normal(ny)
+        if not pressure:
+            rows[k, 2 * ny:3 * ny] = 0.03 * a * 4 * yy * (1 - yy)
+        rows[k, 3 * ny:4 * ny] = 0.001 * a * rng.standard_normal(ny)
+        rows[k, 4 * ny:4 * ny + nx] = 0.08 * a
+        rows[k, 4 * ny + nx:4 * ny + 2 * nx] = 0.001 * rng.standard_normal(nx)
+        rows[k, 4 * ny + 2 * nx:4 * ny + 3 * nx] = 0.01 * a * rng.standard_normal(nx)
+        rows[k, 4 * ny + 4 * nx:] = 1.0 + 0.01 * rng.standard_normal(ny)
+    return rows
+
+
+def _run(nx, ny, n, resident, right="velocity", arith="fused", dtype="f64", macro_last=False, blocks=0, calls=1,
+         obstacles=None, use_ibb=True, ramp=False):
+    """calls x n updates after the collide-only one; returns populations, launches of the last call, forces, macro."""
+    from lbm_b200.solver import Solver
+    s = Solver(nx, ny, tau=0.58, arith=arith, dtype=dtype, right_wall=right)
+    s.set_tuning("resident", 1 if resident else 0)
+    s.set_tuning("graph", 0)
+    if blocks:
+        s.set_tuning("resident_blocks", blocks)
+    if obstacles:
+        s.set_links(obstacles, use_ibb=use_ibb)
+    rng = np.random.default_rng(3)
+    s.set_populations(W[:, None, None] * (1.0 + 0.02 * rng.standard_normal((9, nx, ny))))
+    rows = _rows(nx, ny, n * calls, 5, right == "pressure")
+    if ramp:                                     # one base row + one factor per update (lbm_set_ramp); rows = iteration numbers
+        s.set_walls(rows[-1:])
+        s.set_ramp(1.0 - np.exp(-np.arange(n * calls + 7) ** 2 / 50.0), 100)
+        first = 103
+    else:
+        s.set_walls(rows)
+        first = 0
+    s.step(1, first, 0)
+    forces = []
+    for c in range(calls):
+        l0 = s.launches
+        s.step(n, first + c * n, 1, macro_last=macro_last)
+        launches = s.launches - l0
+        if obstacles:
+            forces.append(s.forces(0, n))
+    s.sync()
+    out = s.populations("post_collision")
+    mac = s.macro() if macro_last else None
+    s.close()
+    return out, launches, forces, mac
+
+
+@pytest.mark.parametrize("nx,ny", [(200, 200), (17, 70), (50, 130), (3, 3), (600, 40), (40, 600), (1073, 200)])
+@pytest.mark.parametrize("right", ["velocity", "pressure"])
+def test_resident_batch_equals_single_updates(nx, ny, right):
+    """(600, 40): several columns in one pass of a block; (40, 600): a column taller than a block; (1073, 200): more
+    columns than resident blocks, several passes; (3, 3): every cell on a wall."""
+    n = 9
+    a, la, _, _ = _run(nx, ny, n, True, right)
+    b, lb, _, _ = _run(nx, ny, n, False, right)
+    assert la == 1 and lb == n
+    assert np.array_equal(a, b), float(np.max(np.abs(a - b)))
+
+
+@pytest.mark.parametrize("arith,dtype", [("strict", "f64"), ("fused", "f32"), ("strict", "f32")])
+def test_resident_batch_other_arithmetic(arith, dtype):
+    a, la, _, _ = _run(97, 150, 12, True, "pressure", arith=arith, dtype=dtype)
+    b, lb, _, _ = _run(97, 150, 12, False, "pressure", arith=arith, dtype=dtype)
+    assert la == 1 and lb == 12
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("blocks", [1, 2, 3])
+def test_resident_batch_block_budgets_and_repeated_launches(blocks):
+    """1 / 2 / 3 resident blocks per SM (3 = the 80-register build); three launches of 7 updates: the progress words are
+    reset per launch and the buffers change roles from launch to launch; the last update alone when macro output is asked."""
+    a, la, _, ma = _run(536, 100, 8, True, blocks=blocks, calls=3, macro_last=True)
+    b, lb, _, mb = _run(536, 100, 8, False, calls=3, macro_last=True)
+    assert la == 2 and lb == 8                  # 7 resident updates + the update that writes rho, u
+    assert np.array_equal(a, b)
+    assert np.array_equal(ma[0], mb[0]) and np.array_equal(ma[1], mb[1])
+
+
+def test_resident_batch_with_ramp_table():
+    a, la, _, _ = _run(200, 200, 11, True, ramp=True, calls=2)
+    b, lb, _, _ = _run(200, 200, 11, False, ramp=True, calls=2)
+    assert la == 1 and lb == 11
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("use_ibb", [True, False])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_resident_batch_with_one_link_group(use_ibb, dtype):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "run_turek30.npz"))
+    obs = [cases.Obstacle(z["boundary"], z["ibb"])]
+    a, la, fa, _ = _run(160, 30, 21, True, "pressure", obstacles=obs, use_ibb=use_ibb, dtype=dtype, calls=2)
+    b, lb, fb, _ = _run(160, 30, 21, False, "pressure", obstacles=obs, use_ibb=use_ibb, dtype=dtype, calls=2)
+    assert la == 1 and lb == 21
+    assert np.array_equal(a, b)
+    for x, y in zip(fa, fb):
+        assert np.array_equal(x, y) and np.max(np.abs(x)) > 1e-6
+
+
+@pytest.mark.parametrize("which", ["turek100", "turek200", "array"])
+def test_resident_batch_reference_cases_at_real_size(which):
+    """BASELINE configs 2-4 (234 / 468 / 8 x 116 links: one, two and several link groups; the array's groups span
+    several bodies) with their own lattice sizes: populations and the drag/lift of every update."""
+    c = {"turek100": lambda: cases.Turek(L_lbm=100), "turek200": lambda: cases.Turek(L_lbm=200, Re_lbm=100.0),
+         "array": lambda: cases.Array()}[which]()
+    a, la, fa, _ = _run(c.nx, c.ny, 33, True, "pressure", obstacles=c.obstacles, blocks=3 if which == "array" else 0)
+    b, lb, fb, _ = _run(c.nx, c.ny, 33, False, "pressure", obstacles=c.obstacles)
+    assert la == 1 and lb == 33
+    assert np.array_equal(a, b)
+    assert np.array_equal(fa[0], fb[0]) and np.max(np.abs(fa[0])) > 1e-6
+
+
+def test_resident_batch_against_the_oracle():
+    """The resident kernel without a detour over step_kernel: the Turek-type channel of the golden run through the batched
+    driver (one resident launch per batch) against the CPU oracle's loop."""
+    from lbm_b200.lattice import lattice
+    from lbm_b200.run import run
+    from oracle import oracle as orc
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "run_turek30.npz"))
+
+    def mk():
+        c = cases.Turek(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])])
+        c.it_max = 150
+        return c
+    cg, co = mk(), mk()
+    lg = lattice(cg, make_dirs=False)
+    run(lg, cg, batch=64, quiet=True)
+    assert lg._L.lbm_launch_count(lg._handle()) < 100       # 151 iterations: not one launch per update
+    lo = orc.OracleLattice(co)
+    orc.run_loop(lo, co)
+    for k in ("g", "g_up", "rho", "u"):
+        x, y = getattr(lg, k), getattr(lo, k)
+        assert float(np.max(np.abs(x - y)) / np.max(np.abs(y))) < 1e-12, k
+    f, fo = np.array(cg.forces), np.array(co.forces)
+    assert f.shape == fo.shape and np.max(np.abs(f - fo)) < 1e-9
+    lg.close()

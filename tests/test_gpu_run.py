@@ -174,6 +174,7 @@ def test_graph_replay_equals_plain_launches():
     for graph in (1, 0):
         s = Solver(nx, ny, tau=0.62, right_wall="pressure")
         s.set_tuning("graph", graph)
+        s.set_tuning("resident", 0)                # (the default on this size: one resident launch per batch, test_gpu_resident.py)
         s.set_links([cases.Obstacle(z["boundary"], z["ibb"])])
         s.init_equilibrium(1.0, 0.03, 0.0)
         yy = np.linspace(0.0, 1.0, ny)
