@@ -149,9 +149,9 @@ struct lbm_handle {
         int *d_col_a = nullptr, *d_dep_off = nullptr, *d_dep = nullptr;
         unsigned int *d_prog = nullptr;
     } res;
-    bool resident = true;              // lbm_set_tuning("resident", 0) keeps the one-launch-per-update path
-    int resident_blocks = 0;           // blocks per SM (0 = what fits)
-    int resident_flags = 0;
+    int resident = -1;                 // lbm_set_tuning("resident", ..): -1 = where it is the faster form (lattices with obstacle
+                                       // links, measured: profiles/README.md), 1 = every small lattice, 0 = never
+    int resident_blocks = 0;           // blocks per SM: 0 = default (3, the 80-register build), 1 / 2 = the 128-register build
     int64_t resident_timeout_ms = 4000;
     std::vector<int> grp_x0, grp_x1;   // first / last column of each link group
     // accounting
@@ -789,7 +789,7 @@ static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64
 // one of them reads meet the columns the other writes.
 static bool resident_candidate(const lbm_handle *h)
 {
-    return h->resident && h->temporal && !h->tb_force && !h->is_band && h->stream != nullptr && h->cfg.x0 == 0 && h->cfg.nxl == h->cfg.nx &&
+    return (h->resident > 0 || (h->resident < 0 && h->n_cells > 0)) && h->temporal && !h->tb_force && !h->is_band && h->stream != nullptr && h->cfg.x0 == 0 && h->cfg.nxl == h->cfg.nx &&
            h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached &&
            (h->n_obs == 0 || (h->n_cells > 0 && h->n_groups <= 64));
 }
@@ -802,7 +802,8 @@ static int build_resident(lbm_handle *h)
     r.built = true;
     int coop = 0, occ = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
-    if (h->resident_blocks >= 3) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stepr_kernel<T, STRICT, 3>, kBlock, 0));
+    const bool three = h->resident_blocks == 0 || h->resident_blocks >= 3;
+    if (three) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stepr_kernel<T, STRICT, 3>, kBlock, 0));
     else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stepr_kernel<T, STRICT, 2>, kBlock, 0));
     if (h->resident_blocks > 0) occ = std::min(occ, h->resident_blocks);
     const int ng = h->n_obs > 0 ? h->n_groups : 0;
@@ -871,28 +872,12 @@ static int launch_resident_t(lbm_handle *h, int64_t n, int64_t first_row, int64_
     rp.link_fs = h->d_link_fs;
     rp.fs_stride = (long long)h->n_links_total * 2;
     rp.slot0 = slot0;
-    rp.flags = h->resident_flags;
-    static long long *dbg = nullptr;
-    if ((rp.flags & 8) && !dbg) cudaMalloc(&dbg, (size_t)2048 * 64 * 4 * sizeof(long long));
-    rp.dbg = dbg;
     CUDA_TRY(cudaMemsetAsync(r.d_prog, 0, ((size_t)r.n_blocks * kProgStride + kProgStride) * sizeof(unsigned int), h->stream));
     void *args[] = {&pa, &lp, &rp};
-    const void *fn = h->resident_blocks >= 3 ? (const void *)stepr_kernel<T, STRICT, 3> : (const void *)stepr_kernel<T, STRICT, 2>;
+    const bool three = h->resident_blocks == 0 || h->resident_blocks >= 3;
+    const void *fn = three ? (const void *)stepr_kernel<T, STRICT, 3> : (const void *)stepr_kernel<T, STRICT, 2>;
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(r.n_blocks), dim3(kBlock), args, 0, h->stream));
     h->launches++;
-    if ((rp.flags & 8) && n >= 200) {
-        cudaStreamSynchronize(h->stream);
-        std::vector<long long> hd((size_t)r.n_blocks * 64 * 4);
-        cudaMemcpy(hd.data(), dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        for (int b : {0, 1, r.n_col_blocks / 2, r.n_col_blocks - 1, r.n_blocks - 1}) {
-            double w = 0, c = 0, p = 0, tot = 0;
-            for (int k = 1; k < 64; k++) {
-                const long long *d = &hd[((size_t)b * 64 + k) * 4], *dp = d - 4;
-                w += d[1] - d[0]; c += d[2] - d[1]; p += d[3] - d[2]; tot += d[0] - dp[0];
-            }
-            fprintf(stderr, "[resident dbg] block %d of %d: wait %.0f compute %.0f publish %.0f | per update %.0f cycles\n", b, r.n_blocks, w / 63, c / 63, p / 63, tot / 63);
-        }
-    }
     return LBM_OK;
 }
 
@@ -1648,13 +1633,12 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->tmap_rows = 0;
         for (bool &b : h->wave_attr_set) b = false;
     } else if (!strcmp(key, "resident")) {
-        h->resident = value != 0;
+        if (value < -1 || value > 1) return fail(LBM_E_INVALID, "resident must be -1 (auto), 0 or 1");
+        h->resident = (int)value;
     } else if (!strcmp(key, "resident_blocks")) {
         if (value < 0 || value > 32) return fail(LBM_E_INVALID, "resident_blocks must be in [0, 32] (blocks per SM, 0 = what fits)");
         h->resident_blocks = (int)value;
         free_resident(h);
-    } else if (!strcmp(key, "resident_flags")) {
-        h->resident_flags = (int)value;
     } else if (!strcmp(key, "resident_timeout_ms")) {
         if (value < 1) return fail(LBM_E_INVALID, "resident_timeout_ms must be positive");
         h->resident_timeout_ms = value;

@@ -1,25 +1,38 @@
 // resident.cuh -- stepr_kernel: a whole BATCH of lattice updates in one launch on a small lattice.
 //
 // The reference's own cases (cavity 200^2, Turek 2D-1/2D-2, the array: 2.9-15.5 MB of populations, BASELINE configs
-// 1-4) are launch bound: an update is ~1 us of work, and a kernel boundary per update -- even as a CUDA-graph node
-// with programmatic dependent launch -- costs more than the update itself.  Here the grid stays resident for the
-// whole batch (cooperative launch: every block is on an SM) and the kernel boundary becomes a NEIGHBOUR hand-shake:
+// 1-4) live in L2, and a kernel boundary per update -- even as a CUDA-graph node with programmatic dependent launch
+// -- is a large part of the 2.6-7 us an update takes.  Here the grid stays resident for the whole batch (cooperative
+// launch: every block is on an SM) and the kernel boundary becomes a NEIGHBOUR hand-shake:
 //
 //   * block b < n_col_blocks owns the columns [col_a[b], col_a[b+1]) in every update; each remaining block owns one
 //     group of obstacle boundary cells (the link groups of lbm_set_links; column blocks skip the masked cells);
-//   * the populations stay in the two global buffers -- these lattices live in L2 -- and are read with ld.global.cg:
-//     L2 is the point of coherence, no L1 line or non-coherent load can be stale inside the launch;
+//   * the populations stay in the two global buffers and are read with ld.global.cg (strong, served by L2): L2 is
+//     the point of coherence, no L1 line or non-coherent load can be stale inside the launch;
 //   * after update k a block publishes k+1 in its progress word (bar.sync, then st.release.gpu by one thread); before
 //     update k it waits until every block it DEPENDS on has published k (ld.relaxed.gpu polls + fence.acq_rel.gpu, one
-//     thread per dependency, then bar.sync).  i depends on j when i reads columns that j writes or the other way round (host side:
-//     column blocks read one column beyond their own, link groups two -- the interpolated bounce-back stencil,
-//     nb.py:98-104).  The relation is symmetric, and with the two buffers alternating that one condition orders both
-//     the reads of update k after the neighbours' writes of update k-1 and the writes of update k after the neighbours'
-//     reads of update k-1.  There is no grid-wide barrier: a block only waits for its neighbours, distant blocks may be
-//     several updates apart;
+//     thread per dependency, then bar.sync).  i depends on j when i reads columns that j writes or the other way round
+//     (host side: column blocks read one column beyond their own -- two at the lattice's left / right wall, where a
+//     corner cell looks at its neighbour's pulled populations --, link groups two: the interpolated bounce-back
+//     stencil, nb.py:98-104).  The relation is symmetric, and with the two buffers alternating that one condition
+//     orders both the reads of update k after the neighbours' writes of update k-1 and the writes of update k after
+//     the neighbours' reads of update k-1.  There is no grid-wide barrier: a block only waits for its neighbours,
+//     distant blocks may be several updates apart;
 //   * a wait that does not come true within `timeout_clk` cycles (a bug, or a grid that is not co-resident) sets the
 //     abort word and the host's error word, and every block leaves at its next wait instead of hanging the device
 //     (lbm_sync reports it).
+//
+// What it buys, measured (tools/resident_bench.py, tools/probe/l2_handshake.cu on B200): an L2 load takes 488 cycles,
+// a relaxed flag store seen by a polling load 930, with the release / acquire fences that make the data visible
+// 2000-2700 -- the hand-shake costs as much as the update.  Lattices with obstacle links gain 14-24 % over graph
+// replay (their link blocks' chain of dependent loads no longer sits behind a kernel boundary): Turek 2D-1 4.8 -> 4.1
+// us per update, 2D-2 7.0 -> 5.3, array 6.2 -> 5.3; the obstacle-free cavity loses (2.6 -> 3.1), so `resident = auto`
+// uses this kernel only where there are links.  A second form without flags and fences -- value and sequence number
+// in ONE store ("LL" entries) for the three populations that cross a block interface, link operands and corner inputs
+// through per-operand entries, rings of four versions -- was built, was bit-identical too and was SLOWER (4-12 us): the
+// per-entry polls and the extra L2 traffic of 16-byte entries cost more than the fences they replace.  Configs 3-4 move
+// 26-31 MB per update through L2 (~7 TB/s in either form): what is left for them is keeping the populations in shared
+// memory.
 //
 // Same per-cell functions as step_kernel (finish_cell_w; ibb_value restates link_block's expressions operation by
 // operation), hence bit-identical to single updates (tests/test_gpu_resident.py).  The per-link momentum-exchange
@@ -48,8 +61,6 @@ template <typename T> struct ResidentParams {
     double *link_fs;                    // per-link terms of update k at link_fs + (slot0 + k) * fs_stride
     long long fs_stride, slot0;
     long long buf_delta;                // elements from the source buffer of update 0 to its destination buffer
-    long long *dbg;                     // [gridDim.x][64][4] clock samples of thread 0 (flags & 8)
-    int flags;                          // experiments (lbm_set_tuning "resident_flags"): see resident_publish / resident_wait
 };
 
 // nb.py:98-100 (kind 1), 102-104 (kind 2), 117 (kind 0) with the precomputed coefficients of lbm_set_links
@@ -148,7 +159,7 @@ __device__ __forceinline__ bool resident_wait(const ResidentParams<T> &rp, const
             }
         }
     }
-    if (my_dep && !(rp.flags & 2)) asm volatile("fence.acq_rel.gpu;" ::: "memory");  // polls + fence = acquire of the neighbours' releases
+    if (my_dep) asm volatile("fence.acq_rel.gpu;" ::: "memory");  // polls + fence = acquire of the neighbours' releases
     if (__syncthreads_and(ok)) return true;
     if (threadIdx.x == 0) {
         atomicExch(abort_w, 1u);
@@ -160,14 +171,10 @@ __device__ __forceinline__ bool resident_wait(const ResidentParams<T> &rp, const
 
 // Every thread's stores of this update are issued (bar.sync) and published by one thread: the release is cumulative over
 // what the barrier ordered.
-__device__ __forceinline__ void resident_publish(unsigned int *my_prog, unsigned int done, int flags)
+__device__ __forceinline__ void resident_publish(unsigned int *my_prog, unsigned int done)
 {
-    if (flags & 1) __threadfence();             // every thread fences its own stores
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (flags & 4) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_prog), "r"(done) : "memory");
-        else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(my_prog), "r"(done) : "memory");
-    }
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(my_prog), "r"(done) : "memory");
 }
 
 // Wall row, ramp factor and force slot of update k of the launch.
@@ -206,17 +213,10 @@ stepr_kernel(const __grid_constant__ StepParams<T> pa /* source / destination bu
             const T *walls, *scale;
             double *f;
             resident_inputs<T>(rp, k, walls, scale, f);     // (before the wait: off the critical path)
-            const long long c0 = clock64();
             if (k > 0 && !resident_wait<T>(rp, my_dep, d0, d1, (unsigned int)k, abort_w)) return;   // (update 0 follows the previous launch in stream order)
-            const long long c1 = clock64();
             const long long sshift = (k & 1) ? rp.buf_delta : 0, dshift = (k & 1) ? -rp.buf_delta : 0;
             resident_columns<T, STRICT>(pa, walls, scale, x0, y0, x_end, sshift, dshift);
-            const long long c2 = clock64();
-            resident_publish(my_prog, (unsigned int)(k + 1), rp.flags);
-            if ((rp.flags & 8) && threadIdx.x == 0 && k >= 100 && k < 164) {
-                long long *d = rp.dbg + ((size_t)b * 64 + (k - 100)) * 4;
-                d[0] = c0; d[1] = c1; d[2] = c2; d[3] = clock64();
-            }
+            resident_publish(my_prog, (unsigned int)(k + 1));
         }
     } else {
         // ---- a link group ------------------------------------------------------------------------
@@ -248,7 +248,7 @@ stepr_kernel(const __grid_constant__ StepParams<T> pa /* source / destination bu
             if (k > 0 && !resident_wait<T>(rp, my_dep, d0, d1, (unsigned int)k, abort_w)) return;
             const long long sshift = (k & 1) ? rp.buf_delta : 0, dshift = (k & 1) ? -rp.buf_delta : 0;
             resident_links<T, STRICT>(pa, walls, scale, f, rl, sval, sqb, sshift, dshift);
-            resident_publish(my_prog, (unsigned int)(k + 1), rp.flags);       // (its barrier also frees sval for the next update)
+            resident_publish(my_prog, (unsigned int)(k + 1));       // (its barrier also frees sval for the next update)
         }
     }
 }

@@ -12,12 +12,11 @@ from lbm_b200 import cases
 from lbm_b200.solver import Solver
 
 
-def run(c, resident, blocks, n=1024, reps=6, dtype="f64", flags=0):
+def run(c, resident, blocks, n=1024, reps=6, dtype="f64"):
     s = Solver(c.nx, c.ny, tau=0.56, right_wall="pressure" if c.obstacles else "velocity", dtype=dtype)
     s.set_tuning("resident", resident)
     if blocks:
         s.set_tuning("resident_blocks", blocks)
-    s.set_tuning("resident_flags", flags)
     if c.obstacles:
         s.set_links(c.obstacles)
     if c.obstacles:
@@ -51,9 +50,6 @@ if __name__ == "__main__":
         for b in (1, 2, 3):
             r, cr = run(c, 1, b, n)
             out.append("resident/%d %.2f us%s" % (b, r, "" if cr == cg else " CHECKSUM DIFFERS"))
-        for fl in (1, 5, 3, 7, 6):
-            r, cr = run(c, 1, 2, n, flags=fl)
-            out.append("flags%d %.2f us%s" % (fl, r, "" if cr == cg else " X"))
         r32, _ = run(c, 1, 0, n, dtype="f32")
         out.append("f32 %.2f us" % r32)
         print("  ".join(out), flush=True)
