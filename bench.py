@@ -250,7 +250,9 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------
 def small_configs(n_dev=4096, n_drv=8192):
     """Per config: device us per update (lbm_step batches, drag/lift of every update stored on the device)
-    and us per iteration of a whole run through lbm_b200.run.run with the app's per-iteration observers."""
+    and us per iteration of whole runs through lbm_b200.run.run with the app's per-iteration observers: a run of n_drv
+    and one of 3 n_drv iterations -- their difference is what an iteration costs once a run is under way, the rest the
+    one-off cost of a run (library handle, inlet-model detection, iteration 0 phase by phase, graph capture)."""
     import torch
     from lbm_b200 import _capi as C
     from lbm_b200 import cases
@@ -263,32 +265,39 @@ def small_configs(n_dev=4096, n_drv=8192):
     out = []
     for name, mk in makers:
         res = None
-        for n_it in (64, n_drv):                          # first pass: warm-up (allocations, graph capture)
+        t_runs = {}
+        for n_it in (64, n_drv, 3 * n_drv):               # first pass: warm-up (allocations, module state)
             c = mk()
             c.it_max = n_it - 1
             lat = lattice(c, make_dirs=False)
             t0 = time.perf_counter()
             n = run(lat, c, batch=1024, quiet=True)
             torch.cuda.synchronize()
-            t_run = time.perf_counter() - t0
+            t_runs[n] = time.perf_counter() - t0
+            if n_it != n_drv:
+                lat.close()
+                continue
             L, h = lat._L, lat._h
             row = np.ascontiguousarray(lat._row[None, :])
             C.check(L.lbm_set_walls(h, 1, row.ctypes.data))
             C.check(L.lbm_sync(h))
-            m = 1024 if n_it > 64 else 64
-            C.check(L.lbm_step(h, m, 0, 0, 0))            # capture
+            m = 1024
+            C.check(L.lbm_step(h, m, 0, 0, 0))            # (graph capture / table build)
             C.check(L.lbm_sync(h))
             t0 = time.perf_counter()
             done = 0
-            while done < (n_dev if n_it > 64 else 64):
+            while done < n_dev:
                 C.check(L.lbm_step(h, m, 0, 0, 0))
                 done += m
             C.check(L.lbm_sync(h))
             t_raw = time.perf_counter() - t0
             res = {"config": name, "nx": c.nx, "ny": c.ny, "links": int(sum(len(o.boundary) for o in c.obstacles)),
-                   "device_us_per_update": t_raw / done * 1e6, "device_mlups": c.nx * c.ny * done / t_raw / 1e6,
-                   "driver_us_per_iteration": t_run / n * 1e6, "driver_mlups": c.nx * c.ny * n / t_run / 1e6}
+                   "device_us_per_update": t_raw / done * 1e6, "device_mlups": c.nx * c.ny * done / t_raw / 1e6}
             lat.close()
+        (n1, t1), (n2, t2) = sorted(t_runs.items())[1:]
+        per_it = (t2 - t1) / (n2 - n1)
+        res.update({"driver_us_per_iteration": per_it * 1e6, "driver_mlups": c.nx * c.ny / per_it / 1e6,
+                    "driver_one_off_ms": (t1 - n1 * per_it) * 1e3, "driver_whole_run_us_per_iteration": t2 / n2 * 1e6})
         # the drop-in mode: the reference's run() phase order (run.py:27-48), one library call per phase from Python
         c = mk()
         lat = lattice(c, make_dirs=False)
@@ -309,11 +318,14 @@ def small_configs(n_dev=4096, n_drv=8192):
         lat.close()
         out.append(res)
     return {"configs": out, "note": "L2-resident lattices (2.9-15.5 MB): launch/latency bound, a percentage of the HBM roofline is nominal there; "
-                                    "device = CUDA-graph replay of 1024-update batches, drag/lift of every update summed on the device; "
-                                    "driver = whole run of %d iterations through lbm_b200.run.run (batches of 1024 updates, one ramp scalar "
-                                    "per iteration from the host, per-iteration callbacks of the app replayed; includes the one-off graph "
-                                    "capture); per_phase = the reference's own run() loop order on the drop-in lattice class (one fused "
-                                    "update per macro() call, drag/lift fetched every iteration)" % n_drv}
+                                    "device = lbm_step batches of 1024 updates, drag/lift of every update summed on the device: CUDA-graph replay "
+                                    "(obstacle-free lattices) or one resident launch per batch (stepr_kernel, lattices with obstacle links); "
+                                    "driver = whole runs of %d and %d iterations through lbm_b200.run.run (batches of 1024 updates, one ramp scalar "
+                                    "per iteration from the host, per-iteration callbacks of the app replayed on the host while the device "
+                                    "executes the next batch): driver_us_per_iteration = difference of the two runs per iteration, "
+                                    "driver_one_off_ms = the rest (handle, inlet-model detection, iteration 0, graph capture), "
+                                    "driver_whole_run = the longer run all told; per_phase = the reference's own run() loop order on the drop-in lattice class (one fused "
+                                    "update per macro() call, drag/lift fetched every iteration)" % (n_drv, 3 * n_drv)}
 
 
 # ------------------------------------------------------------------------------------------

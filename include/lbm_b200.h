@@ -205,6 +205,11 @@ int lbm_apply_bc(lbm_t *h, int64_t row);
  * reads slots first..first+n-1 written by the last lbm_step; lbm_forces_now evaluates the
  * current F directly (what lattice.drag_lift sees right after set_bc).  out: [n][n_obs][2]. */
 int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out);
+/* lbm_get_forces without the wait: the sums of the last lbm_step are reduced and copied to `out_pinned` (page-locked
+ * host memory) on the handle's stream; they are there once the stream has passed this point (an event recorded
+ * after the call).  Lets the caller enqueue the next batch of updates before the host looks at this one's drag/lift
+ * (lbm_b200/run.py: the apps' per-iteration callbacks, turek.py:147-162, overlap the device's next batch).  f64 only. */
+int lbm_get_forces_async(lbm_t *h, int64_t first, int64_t n, double *out_pinned);
 int lbm_forces_now(lbm_t *h, double *out);
 
 int lbm_get_populations(lbm_t *h, int32_t which, void *host);

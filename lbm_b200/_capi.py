@@ -80,6 +80,7 @@ SIGNATURES = {
     "lbm_set_tuning": (ctypes.c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "lbm_apply_bc": (ctypes.c_int, [c_vp, c_i64]),
     "lbm_get_forces": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
+    "lbm_get_forces_async": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
     "lbm_forces_now": (ctypes.c_int, [c_vp, c_vp]),
     "lbm_get_populations": (ctypes.c_int, [c_vp, c_i32, c_vp]),
     "lbm_get_macro": (ctypes.c_int, [c_vp, c_vp, c_vp]),

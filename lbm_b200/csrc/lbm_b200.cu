@@ -153,6 +153,7 @@ struct lbm_handle {
                                        // links, measured: profiles/README.md), 1 = every small lattice, 0 = never
     int resident_blocks = 0;           // blocks per SM: 0 = default (3, the 80-register build), 1 / 2 = the 128-register build
     int64_t resident_timeout_ms = 4000;
+    int clock_khz = 0;                 // (cudaDevAttrClockRate is a slow query -- up to 100 ms, measured --: asked once)
     std::vector<int> grp_x0, grp_x1;   // first / last column of each link group
     // accounting
     int64_t launches = 0;
@@ -861,9 +862,8 @@ static int launch_resident_t(lbm_handle *h, int64_t n, int64_t first_row, int64_
     rp.col_a = r.d_col_a; rp.dep_off = r.d_dep_off; rp.dep = r.d_dep;
     rp.prog = r.d_prog;
     rp.err = h->d_err;
-    int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
-    rp.timeout_clk = (long long)h->resident_timeout_ms * std::max(khz, 1000000);
+    if (!h->clock_khz) cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, h->cfg.device);
+    rp.timeout_clk = (long long)h->resident_timeout_ms * std::max(h->clock_khz, 1000000);
     rp.walls = static_cast<const T *>(h->walls);
     rp.row_len = h->row_len; rp.wall_rows = std::max<int64_t>(h->wall_rows, 1);
     rp.first_row = first_row; rp.row_stride = row_stride;
@@ -1711,6 +1711,18 @@ int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
             if (first + s == 0 && h->force_skip0) continue;      // never produced by link blocks
             for (int k = 0; k < 2 * nobs; k++) out[s * 2 * nobs + k] += h->force_const[k];
         }
+    return LBM_OK;
+}
+
+int lbm_get_forces_async(lbm_t *h, int64_t first, int64_t n, double *out_pinned)
+{
+    CHECK_H(h);
+    if (!out_pinned || first < 0 || n < 0 || first + n > h->force_n) return fail(LBM_E_INVALID, "force slots [%lld, %lld) not available (%lld written)", (long long)first, (long long)(first + n), (long long)h->force_n);
+    if (!h->force_const.empty()) return fail(LBM_E_UNSUPPORTED, "lbm_get_forces_async: f32 storage adds a host-side constant to the sums; use lbm_get_forces");
+    const int nobs = std::max(h->n_obs, 1);
+    if (n == 0) return LBM_OK;
+    { int rc = reduce_dirty_forces(h); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(out_pinned, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     return LBM_OK;
 }
 

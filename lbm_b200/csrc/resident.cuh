@@ -24,10 +24,11 @@
 //
 // What it buys, measured (tools/resident_bench.py, tools/probe/l2_handshake.cu on B200): an L2 load takes 488 cycles,
 // a relaxed flag store seen by a polling load 930, with the release / acquire fences that make the data visible
-// 2000-2700 -- the hand-shake costs as much as the update.  Lattices with obstacle links gain 14-24 % over graph
-// replay (their link blocks' chain of dependent loads no longer sits behind a kernel boundary): Turek 2D-1 4.8 -> 4.1
-// us per update, 2D-2 7.0 -> 5.3, array 6.2 -> 5.3; the obstacle-free cavity loses (2.6 -> 3.1), so `resident = auto`
-// uses this kernel only where there are links.  A second form without flags and fences -- value and sequence number
+// 2000-2700 -- the hand-shake costs as much as the update.  Lattices with obstacle links gain 17-26 % over graph
+// replay (their link blocks' chain of dependent loads no longer sits behind a kernel boundary): Turek 2D-1 4.72 -> 3.93
+// us per update, 2D-2 6.97 -> 5.13, array 6.17 -> 5.08 (median of 100 launches of 1024 updates, p90 within 0.5 % of
+// it: tools/resident_jitter.py); the obstacle-free cavity loses (2.6 -> 3.0), so `resident = auto` uses this kernel
+// only where there are links.  A pause between two polls (__nanosleep) changes nothing.  A second form without flags and fences -- value and sequence number
 // in ONE store ("LL" entries) for the three populations that cross a block interface, link operands and corner inputs
 // through per-operand entries, rings of four versions -- was built, was bit-identical too and was SLOWER (4-12 us): the
 // per-entry polls and the extra L2 traffic of 16-byte entries cost more than the fences they replace.  Configs 3-4 move

@@ -390,6 +390,7 @@ class lattice:
             # (pageable host memory: the copy has left the host buffer when the call returns -- no stream sync)
             C.check(self._L.lbm_set_walls(self._handle(), 1, self._ptr(self._row)))
             self._row_dev = self._row.copy()
+            self._base_dev = None
 
     def _push_links(self):
         obs = self._obstacles
@@ -495,6 +496,52 @@ class lattice:
         self._cache = {}
         return forces
 
+    # -- the same batch in two halves: enqueue now, look at the drag/lift sums later.  run.py enqueues the NEXT batch in
+    # between, so that the apps' per-iteration callbacks of one batch run on the host while the device executes the
+    # next one (whole runs of the reference's small cases are otherwise the SUM of device and host time).
+    def can_pipeline(self):
+        return self.dtype == "f64"          # (f32 storage: lbm_get_forces adds a host-side constant, no asynchronous form)
+
+    def batch_enqueue_ramp(self, base_row, scales):
+        """batch_updates_ramp without the wait; returns a token for batch_result().  At most two batches in flight."""
+        if self._state != "streamed":
+            raise C.LbmError(-3, "batch_updates() must follow set_bc")
+        self._need_all_bcs()
+        self._push_links()
+        h = self._handle()
+        torch = self._torch
+        scales = np.ascontiguousarray(scales, dtype=np.float64).reshape(-1)
+        n = scales.size
+        nobs = max(len(self._link_obstacles), 1)
+        slot = self._pipe_slot = getattr(self, "_pipe_slot", 1) ^ 1
+        pool = self.__dict__.setdefault("_pipe_pool", [None, None])
+        if pool[slot] is None or pool[slot][0].numel() < n or pool[slot][1].shape[1] != nobs or pool[slot][1].shape[0] < n:
+            pool[slot] = (torch.empty(max(n, 64), dtype=torch.float64).pin_memory(),
+                          torch.empty((max(n, 64), nobs, 2), dtype=torch.float64).pin_memory())
+        ramp, forces = pool[slot]
+        ramp.numpy()[:n] = scales                # (page-locked: the copies below do not wait for the stream)
+        base_row = np.ascontiguousarray(base_row, dtype=np.float64).reshape(-1)
+        if self._row_dev is not None or getattr(self, "_base_dev", None) is None or not np.array_equal(self._base_dev, base_row):
+            C.check(self._L.lbm_set_walls(h, 1, self._ptr(base_row)))    # (not again when batch follows batch)
+            self._base_dev = base_row.copy()
+        self._row_dev = None
+        C.check(self._L.lbm_set_ramp(h, C.c_vp(ramp.data_ptr()), 0, n))
+        C.check(self._L.lbm_step(h, n, 0, 1, C.LBM_STEP_MACRO_LAST))
+        C.check(self._L.lbm_get_forces_async(h, 0, n, C.c_vp(forces.data_ptr())))
+        ev = torch.cuda.Event()
+        ev.record(self._stream)
+        C.check(self._L.lbm_set_ramp(h, None, 0, 0))
+        self.updates += n
+        self._state = "macro_done"
+        self._cache = {}
+        return (ev, forces, n)
+
+    def batch_result(self, token):
+        """[n, n_obs, 2] momentum-exchange sums of an enqueued batch (waits for that batch only)."""
+        ev, forces, n = token
+        ev.synchronize()
+        return forces.numpy()[:n].copy()
+
     def forces_now(self):
         """[n_obs, 2] momentum-exchange sums of the current post-collision array."""
         self._push_links()
@@ -557,24 +604,28 @@ class lattice:
             self._obstacles = list(obstacles)
             self._links_key = None
 
-    def save_state(self):
-        """Device-side copy of the current post-collision populations (for exact stop-rule rollback)."""
+    def save_state(self, slot=0):
+        """Device-side copy of the current post-collision populations (for exact stop-rule rollback); slot 0 / 1:
+        the pipelined driver keeps the starting states of two batches."""
         cur = C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
         src = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
-        if getattr(self, "_saved", None) is None:
-            self._saved = self._torch.empty_like(src)
+        saved = self.__dict__.setdefault("_saved", {})
+        if slot not in saved:
+            saved[slot] = [self._torch.empty_like(src), 0]
         # on the library's stream: ordered after the updates already enqueued and before the next ones
         # (a copy on torch's current stream would race with them: the handle's stream is non-blocking)
         with self._torch.cuda.stream(self._stream):
-            self._saved.copy_(src)
+            saved[slot][0].copy_(src)
+        saved[slot][1] = self.updates
 
-    def restore_state(self):
+    def restore_state(self, slot=0):
         cur = C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
         dst = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
         with self._torch.cuda.stream(self._stream):
-            dst.copy_(self._saved)
+            dst.copy_(self._saved[slot][0])
+        self.updates = self._saved[slot][1]
         self._cache = {}
 
     # ------------------------------------------------------------------------------------

@@ -15,6 +15,17 @@ the updates stored.  What the app sees is identical to the per-phase loop:
     rule fires inside a batch, the populations are rolled back to the batch start and re-run up to
     that iteration (the update is deterministic).
 
+Pipelining (default where the lattice offers batch_enqueue_ramp and the inlet model fits): a batch is enqueued and the
+host does NOT wait for it; it records the boundary conditions of the batch's last iteration (set_inlets / set_bc: host
+bookkeeping only), enqueues the NEXT batch, and only then fetches the first batch's drag/lift sums and replays its
+callbacks -- while the device executes the next batch.  The drag/lift of a batch's last iteration is slot 0 of the
+following batch (the sums of iteration i are produced by update i+1), so that iteration's observables / check_stop are
+replayed with the next batch.  A whole run then costs max(device, host) per iteration instead of their sum.  The
+speculation is given up where the app needs the fields (output iterations), at it_max, and when an 'obs' stop fires:
+the populations are rolled back to the start of the batch the stop lies in, exactly as without pipelining.  The app sees
+the same calls with the same values; only set_inlets / set_bc of a batch's last iteration come before the replay of
+that batch's earlier iterations.
+
 The reference's own run() also works with lbm_b200.lattice.lattice (one update per iteration).
 """
 import math
@@ -96,7 +107,96 @@ def _tail_of_iteration(lattice, app, it):
     return app.check_stop(it)
 
 
-def run(lattice, app, batch=512, quiet=False, inlet_model=True):
+def _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_time):
+    """The batched loop with one batch in flight while the previous one is replayed (module docstring)."""
+    exact_stop = not stop_on_it
+    it_max = int(app.it_max) if stop_on_it and hasattr(app, "it_max") else None
+
+    def size(it):
+        n = max(1, int(batch))
+        if freq > 0:
+            n = min(n, (-it) % freq + 1 if it % freq else 1)
+        if it_max is not None:
+            n = max(1, min(n, it_max - it + 1))
+        return n
+
+    serial = [0]
+
+    def enqueue(it, carry):
+        """Updates of iterations it .. it+n-1; needs the boundary conditions of iteration it-1 recorded."""
+        n = size(it)
+        if not np.array_equal(lattice._row, model.row(it - 1)):
+            raise RuntimeError("inlet model no longer matches app.set_inlets at iteration %d" % (it - 1))
+        scales = model.scales(np.arange(it - 1, it - 1 + n))
+        slot = serial[0] & 1
+        serial[0] += 1
+        if exact_stop:
+            lattice.save_state(slot)
+        return dict(it=it, n=n, last=it + n - 1, scales=scales, slot=slot, carry=carry,
+                    token=lattice.batch_enqueue_ramp(model.base, scales))
+
+    def callbacks(j, f):
+        if not quiet:
+            app.printings(j)
+        lattice._replay = f
+        try:
+            app.outputs(lattice, j)                           # no-op off the output iterations
+            app.observables(lattice, j)
+        finally:
+            lattice._replay = None
+        return app.check_stop(j)
+
+    cur = enqueue(1, False)
+    while True:
+        it, n, last = cur["it"], cur["n"], cur["last"]
+        chain = not (freq > 0 and last % freq == 0) and not (it_max is not None and last >= it_max)
+        nxt = None
+        if chain:
+            # iteration `last`: its boundary conditions are host bookkeeping; its drag/lift arrives with the next batch
+            app.set_inlets(lattice, last)
+            lattice.collision_stream()
+            app.set_bc(lattice)
+            nxt = enqueue(last + 1, True)
+        forces = lattice.batch_result(cur["token"])           # slot k = iteration it+k-1
+        stopped_at = None
+        for k in range(0 if cur["carry"] else 1, n):
+            if not callbacks(it + k - 1, forces[k]):
+                stopped_at = it + k - 1
+                break
+        if stopped_at is not None:
+            # the stop rule fired: back to the start of this batch, redo it .. stopped_at exactly
+            if nxt is not None:
+                lattice.batch_result(nxt["token"])            # (speculated in vain)
+            m = stopped_at - it + 1
+            lattice.restore_state(cur["slot"])
+            lattice._state = "streamed"
+            if m > 0:
+                lattice.batch_updates_ramp(model.base, cur["scales"][:m])
+            else:
+                lattice._state = "macro_done"                 # (the iteration before the batch: its update is the saved state)
+            lattice.collision_stream()
+            app.set_inlets(lattice, stopped_at)
+            app.set_bc(lattice)
+            it = stopped_at + 1
+            break
+        if chain:
+            cur = nxt
+            continue
+        if not quiet:
+            app.printings(last)
+        app.set_inlets(lattice, last)
+        if not _tail_of_iteration(lattice, app, last):
+            it = last + 1
+            break
+        cur = enqueue(last + 1, False)
+
+    if not quiet:
+        print("# Loop time = {:f}".format(time.time() - start_time))
+    app.finalize(lattice)
+    return it
+
+
+def run(lattice, app, batch=512, quiet=False, inlet_model=True, pipeline=True):
     app.initialize(lattice)
     model = InletModel.detect(lattice, app) if inlet_model and hasattr(lattice, "batch_updates_ramp") else None
     start_time = time.time()
@@ -114,6 +214,9 @@ def run(lattice, app, batch=512, quiet=False, inlet_model=True):
     lattice.macro()
     compute = _tail_of_iteration(lattice, app, it)
     it = 1
+    if (compute and pipeline and model is not None and hasattr(lattice, "batch_enqueue_ramp") and lattice.can_pipeline()
+            and (exact_stop or hasattr(app, "it_max"))):
+        return _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_time)
 
     while compute:
         # batch = iterations it .. it+n-1; it ends on the next output iteration / it_max

@@ -31,14 +31,15 @@ class ObsStop(cases.Turek):
         return not (len(f) > 40 and abs(f[-1][0] - f[-2][0]) < 2.0e-4)
 
 
-@pytest.mark.parametrize("batch", [1, 7, 64])
-def test_batched_run_equals_per_phase_loop(batch):
+@pytest.mark.parametrize("batch,pipeline", [(1, True), (7, False), (7, True), (64, True)])
+def test_batched_run_equals_per_phase_loop(batch, pipeline):
+    """pipeline: the next batch runs on the device while the callbacks of the previous one are replayed (run.py)."""
     from lbm_b200.lattice import lattice
     from lbm_b200.run import run
     cg, co = _turek30(), _turek30()
     cg.it_max = co.it_max = 130
     lg = lattice(cg, make_dirs=False, arith="strict")
-    n = run(lg, cg, batch=batch, quiet=True)
+    n = run(lg, cg, batch=batch, quiet=True, pipeline=pipeline)
     lo = orc.OracleLattice(co)
     n_ref = orc.run_loop(lo, co)
     assert n == n_ref == 131
@@ -49,12 +50,13 @@ def test_batched_run_equals_per_phase_loop(batch):
     assert np.max(np.abs(f - fo)) <= 1e-13 * np.max(np.abs(fo))
 
 
-def test_batched_run_stops_on_the_same_iteration():
+@pytest.mark.parametrize("pipeline", [False, True])
+def test_batched_run_stops_on_the_same_iteration(pipeline):
     from lbm_b200.lattice import lattice
     from lbm_b200.run import run
     cg, co = _turek30(ObsStop), _turek30(ObsStop)
     lg = lattice(cg, make_dirs=False, arith="strict")
-    n = run(lg, cg, batch=50, quiet=True)
+    n = run(lg, cg, batch=50, quiet=True, pipeline=pipeline)
     lo = orc.OracleLattice(co)
     n_ref = orc.run_loop(lo, co)
     assert n == n_ref and 41 < n < 5000
