@@ -542,8 +542,10 @@ def gpu_arm(args):
                         "bytes_per_launch_moved": BYTES_PER_LUP[args.dtype] * nxl * ny, "updates_per_launch": upl,
                         "kernel": kdesc % args.dtype, "launch_ms": t_launch * 1e3,
                         "fp64_pipe_frac": value / world * 1e6 * FP64_PER_UPDATE / fp64_peak,
-                        "fp64_note": "the multi-update kernel is bound by FP64 issue, not HBM: %d FP64 instructions per cell "
-                                     "update (zero-redundancy count) x LUPS / (148 SMs x 64 lanes x %.0f MHz)" % (FP64_PER_UPDATE, sm_mhz),
+                        "fp64_note": "share of the FP64 lanes the update arithmetic occupies: %d FP64 instructions per cell update "
+                                     "(zero-redundancy count) x LUPS / (148 SMs x 64 lanes x %.0f MHz); the multi-update kernel is "
+                                     "bound by its shared-memory data pipe (72 %%, ncu) and, sustained, by the board's power cap -- "
+                                     "not by HBM and not by FP64 issue (DESIGN.md section 4)" % (FP64_PER_UPDATE, sm_mhz),
                         "per": "rank 0 slab, from the median timed block"},
            "parity": parity,
            "clocks": clocks}
