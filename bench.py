@@ -251,7 +251,7 @@ def reference_arm(args):
 def small_configs(n_dev=4096, n_drv=8192):
     """Per config: device us per update (lbm_step batches, drag/lift of every update stored on the device)
     and us per iteration of whole runs through lbm_b200.run.run with the app's per-iteration observers: a run of n_drv
-    and one of 3 n_drv iterations -- their difference is what an iteration costs once a run is under way, the rest the
+    and one of 5 n_drv iterations -- their difference is what an iteration costs once a run is under way, the rest the
     one-off cost of a run (library handle, inlet-model detection, iteration 0 phase by phase, graph capture)."""
     import torch
     from lbm_b200 import _capi as C
@@ -266,7 +266,7 @@ def small_configs(n_dev=4096, n_drv=8192):
     for name, mk in makers:
         res = None
         t_runs = {}
-        for n_it in (64, n_drv, 3 * n_drv):               # first pass: warm-up (allocations, module state)
+        for n_it in (64, n_drv, 5 * n_drv):               # first pass: warm-up (allocations, module state)
             c = mk()
             c.it_max = n_it - 1
             lat = lattice(c, make_dirs=False)
@@ -325,7 +325,7 @@ def small_configs(n_dev=4096, n_drv=8192):
                                     "executes the next batch): driver_us_per_iteration = difference of the two runs per iteration, "
                                     "driver_one_off_ms = the rest (handle, inlet-model detection, iteration 0, graph capture), "
                                     "driver_whole_run = the longer run all told; per_phase = the reference's own run() loop order on the drop-in lattice class (one fused "
-                                    "update per macro() call, drag/lift fetched every iteration)" % (n_drv, 3 * n_drv)}
+                                    "update per macro() call, drag/lift fetched every iteration)" % (n_drv, 5 * n_drv)}
 
 
 # ------------------------------------------------------------------------------------------
