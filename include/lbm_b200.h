@@ -193,7 +193,11 @@ int lbm_set_temporal_depth(lbm_t *h, int32_t depth);
  * wavefront launch (default: by slab size), "wave_tail" = width of the short chunks that end a
  * wavefront launch (-1 auto, 0 uniform chunks), "wave_rows" = strip height (64 | 128), "pf_ahead" = L2
  * prefetch distance of step2_kernel in blocks, "graph" = 0 disables the CUDA-graph replay of
- * lbm_step batches on small lattices (>= 16 updates, <= 2^19 cells, non-default stream). */
+ * lbm_step batches on small lattices (>= 16 updates, <= 2^19 cells, non-default stream), "resident" =
+ * resident batches on those lattices (one cooperative launch per run of >= 4 updates, stepr_kernel: the
+ * reference's run.py:24-54 loop body executed n times without a kernel boundary): -1 where it is the faster
+ * form (lattices with obstacle links; default), 0 never, 1 always; "resident_blocks" = its blocks per SM
+ * (0 = default), "resident_timeout_ms" = after how long a block-to-block wait gives up (lbm_sync then fails). */
 int lbm_set_tuning(lbm_t *h, const char *key, int64_t value);
 
 /* Stream + (I)BB + Zou-He of the current F with wall row `row`, no collision: materialises the

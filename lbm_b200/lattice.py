@@ -129,6 +129,10 @@ class lattice:
         self._replay = None             # per-obstacle (fx, fy) of the iteration being replayed
         self._link_obstacles = []
         self.updates = 0                # fused updates executed
+        self._base_dev = None           # base row of the ramp form that is on the device (batch follows batch)
+        self._pipe_slot = 1             # pinned ramp / force buffers of the two batches in flight
+        self._pipe_pool = [None, None]
+        self._saved = {}                # slot -> [device copy of the populations, update count]
 
     def _create(self, right_wall):
         torch = self._torch
@@ -463,6 +467,7 @@ class lattice:
         C.check(self._L.lbm_set_walls(h, n, self._ptr(rows)))
         C.check(self._L.lbm_sync(h))
         self._row_dev = None
+        self._base_dev = None
         C.check(self._L.lbm_step(h, n, 0, 1, C.LBM_STEP_MACRO_LAST))
         nobs = max(len(self._link_obstacles), 1)
         forces = np.zeros((n, nobs, 2))
@@ -485,6 +490,7 @@ class lattice:
         n = scales.size
         C.check(self._L.lbm_set_walls(h, 1, self._ptr(base_row)))        # (one row; the per-phase calls reuse the slot)
         self._row_dev = None
+        self._base_dev = base_row.copy()
         C.check(self._L.lbm_set_ramp(h, self._ptr(scales), 0, n))
         C.check(self._L.lbm_step(h, n, 0, 1, C.LBM_STEP_MACRO_LAST))
         nobs = max(len(self._link_obstacles), 1)
@@ -513,15 +519,15 @@ class lattice:
         scales = np.ascontiguousarray(scales, dtype=np.float64).reshape(-1)
         n = scales.size
         nobs = max(len(self._link_obstacles), 1)
-        slot = self._pipe_slot = getattr(self, "_pipe_slot", 1) ^ 1
-        pool = self.__dict__.setdefault("_pipe_pool", [None, None])
+        slot = self._pipe_slot = self._pipe_slot ^ 1
+        pool = self._pipe_pool
         if pool[slot] is None or pool[slot][0].numel() < n or pool[slot][1].shape[1] != nobs or pool[slot][1].shape[0] < n:
             pool[slot] = (torch.empty(max(n, 64), dtype=torch.float64).pin_memory(),
                           torch.empty((max(n, 64), nobs, 2), dtype=torch.float64).pin_memory())
         ramp, forces = pool[slot]
         ramp.numpy()[:n] = scales                # (page-locked: the copies below do not wait for the stream)
         base_row = np.ascontiguousarray(base_row, dtype=np.float64).reshape(-1)
-        if self._row_dev is not None or getattr(self, "_base_dev", None) is None or not np.array_equal(self._base_dev, base_row):
+        if self._row_dev is not None or self._base_dev is None or not np.array_equal(self._base_dev, base_row):
             C.check(self._L.lbm_set_walls(h, 1, self._ptr(base_row)))    # (not again when batch follows batch)
             self._base_dev = base_row.copy()
         self._row_dev = None
@@ -610,7 +616,7 @@ class lattice:
         cur = C.c_vp()
         C.check(self._L.lbm_state_ptrs(self._handle(), ctypes.byref(cur), None))
         src = self._buf[0] if cur.value == self._buf[0].data_ptr() else self._buf[1]
-        saved = self.__dict__.setdefault("_saved", {})
+        saved = self._saved
         if slot not in saved:
             saved[slot] = [self._torch.empty_like(src), 0]
         # on the library's stream: ordered after the updates already enqueued and before the next ones
