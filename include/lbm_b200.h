@@ -273,6 +273,14 @@ int lbm_state_checksum(lbm_t *h, uint64_t *out);
 
 /* Launch counter: kernels launched by this handle since creation (bench.py gpu_launches). */
 int64_t lbm_launch_count(const lbm_t *h);
+/* The block plan of a resident batch (stepr_kernel), computed on the host without a device: nx columns, at most
+ * max_blocks resident blocks, n_groups link groups with boundary cells in columns [grp_x0[g], grp_x1[g]].  Column block
+ * i < *n_col_blocks owns columns [col_a[i], col_a[i+1]), block *n_col_blocks + g is link group g; block b waits for the
+ * blocks dep[dep_off[b] .. dep_off[b+1]) before every update.  col_a: room for max_blocks + 1, dep_off: max_blocks + 1,
+ * dep: dep_cap entries.  For tests/test_resident_plan_cpu.py, which replays the hand-shake with random block timing
+ * and checks that no block reads a column before it was written or overwrites one that is still being read. */
+int lbm_resident_plan(int32_t nx, int32_t max_blocks, int32_t n_groups, const int32_t *grp_x0, const int32_t *grp_x1,
+                      int32_t *n_col_blocks, int32_t *col_a, int32_t *dep_off, int32_t *dep, int64_t dep_cap);
 /* Device time of the updates of the last lbm_step call, from CUDA events recorded on the
  * handle's stream around them (milliseconds; waits for the stream). */
 int lbm_last_step_ms(lbm_t *h, float *ms);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "lbm_peer_signal": (ctypes.c_int, [c_vp]),
     "lbm_state_checksum": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
     "lbm_launch_count": (c_i64, [c_vp]),
+    "lbm_resident_plan": (ctypes.c_int, [c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "lbm_last_step_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
 }
 

@@ -795,6 +795,39 @@ static bool resident_candidate(const lbm_handle *h)
            (h->n_obs == 0 || (h->n_cells > 0 && h->n_groups <= 64));
 }
 
+// The plan itself (no device needed; lbm_resident_plan exports it for tests/test_resident_plan_cpu.py, which replays the
+// hand-shake with random block timing): column block i owns columns [col_a[i], col_a[i+1]) and reads one column beyond
+// them -- two at the lattice's left / right wall: a corner cell takes rho and u from its x-neighbour on the horizontal
+// wall, whose pulled populations come from one column further; link group g owns the boundary cells in columns
+// [grp_x0[g], grp_x1[g]] and reads two columns beyond (interpolated bounce-back, nb.py:98-104).
+struct ResidentPlan {
+    int n_col_blocks = 0;
+    std::vector<int> col_a, dep_off, dep;
+};
+static ResidentPlan plan_resident(int nx, int max_blocks, int ng, const int *grp_x0, const int *grp_x1)
+{
+    ResidentPlan pl;
+    const int ncb = std::min(nx, max_blocks - ng), nb = ncb + ng;
+    pl.n_col_blocks = ncb;
+    pl.col_a.resize(ncb + 1);
+    for (int i = 0; i <= ncb; i++) pl.col_a[i] = (int)((int64_t)i * nx / ncb);
+    struct Iv { int w0, w1, r0, r1; };
+    std::vector<Iv> iv(nb);
+    const std::vector<int> &col_a = pl.col_a;
+    for (int i = 0; i < ncb; i++)
+        iv[i] = {col_a[i], col_a[i + 1] - 1, col_a[i] - (col_a[i + 1] == nx ? 2 : 1), col_a[i + 1] + (col_a[i] == 0 ? 1 : 0)};
+    for (int g = 0; g < ng; g++) iv[ncb + g] = {grp_x0[g], grp_x1[g], grp_x0[g] - 2, grp_x1[g] + 2};
+    auto meets = [](int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; };
+    pl.dep_off.assign(nb + 1, 0);
+    for (int i = 0; i < nb; i++) {
+        for (int j = 0; j < nb; j++)
+            if (j != i && (meets(iv[i].r0, iv[i].r1, iv[j].w0, iv[j].w1) || meets(iv[j].r0, iv[j].r1, iv[i].w0, iv[i].w1)))
+                pl.dep.push_back(j);
+        pl.dep_off[i + 1] = (int)pl.dep.size();
+    }
+    return pl;
+}
+
 template <typename T, bool STRICT>
 static int build_resident(lbm_handle *h)
 {
@@ -810,25 +843,9 @@ static int build_resident(lbm_handle *h)
     const int ng = h->n_obs > 0 ? h->n_groups : 0;
     const int max_blocks = occ * h->n_sm;
     if (!coop || max_blocks - ng < 1) return LBM_OK;                // not usable: the per-update launches stay
-    const int nx = (int)h->cfg.nxl;
-    const int ncb = std::min(nx, max_blocks - ng), nb = ncb + ng;
-    std::vector<int> col_a(ncb + 1);
-    for (int i = 0; i <= ncb; i++) col_a[i] = (int)((int64_t)i * nx / ncb);
-    struct Iv { int w0, w1, r0, r1; };
-    std::vector<Iv> iv(nb);
-    // (a corner cell takes rho and u from its x-neighbour on the horizontal wall, whose pulled populations come from one
-    // column further: the blocks with the first / last lattice column read two columns beyond it)
-    for (int i = 0; i < ncb; i++)
-        iv[i] = {col_a[i], col_a[i + 1] - 1, col_a[i] - (col_a[i + 1] == nx ? 2 : 1), col_a[i + 1] + (col_a[i] == 0 ? 1 : 0)};
-    for (int g = 0; g < ng; g++) iv[ncb + g] = {h->grp_x0[g], h->grp_x1[g], h->grp_x0[g] - 2, h->grp_x1[g] + 2};
-    auto meets = [](int a0, int a1, int b0, int b1) { return a0 <= b1 && b0 <= a1; };
-    std::vector<int> dep_off(nb + 1, 0), dep;
-    for (int i = 0; i < nb; i++) {
-        for (int j = 0; j < nb; j++)
-            if (j != i && (meets(iv[i].r0, iv[i].r1, iv[j].w0, iv[j].w1) || meets(iv[j].r0, iv[j].r1, iv[i].w0, iv[i].w1)))
-                dep.push_back(j);
-        dep_off[i + 1] = (int)dep.size();
-    }
+    ResidentPlan pl = plan_resident((int)h->cfg.nxl, max_blocks, ng, h->grp_x0.data(), h->grp_x1.data());
+    const int ncb = pl.n_col_blocks, nb = ncb + ng;
+    std::vector<int> &col_a = pl.col_a, &dep_off = pl.dep_off, &dep = pl.dep;
     if (dep.empty()) dep.push_back(0);
     CUDA_TRY(cudaMalloc(&r.d_col_a, col_a.size() * sizeof(int)));
     CUDA_TRY(cudaMalloc(&r.d_dep_off, dep_off.size() * sizeof(int)));
@@ -2022,6 +2039,20 @@ int lbm_state_checksum(lbm_t *h, uint64_t *out)
 }
 
 int64_t lbm_launch_count(const lbm_t *h) { return h ? h->launches : 0; }
+
+int lbm_resident_plan(int32_t nx, int32_t max_blocks, int32_t n_groups, const int32_t *grp_x0, const int32_t *grp_x1,
+                      int32_t *n_col_blocks, int32_t *col_a, int32_t *dep_off, int32_t *dep, int64_t dep_cap)
+{
+    if (nx < 1 || n_groups < 0 || max_blocks - n_groups < 1 || (n_groups > 0 && (!grp_x0 || !grp_x1)) || !n_col_blocks || !col_a || !dep_off)
+        return fail(LBM_E_INVALID, "lbm_resident_plan: bad arguments");
+    const ResidentPlan pl = plan_resident(nx, max_blocks, n_groups, grp_x0, grp_x1);
+    if ((int64_t)pl.dep.size() > dep_cap) return fail(LBM_E_INVALID, "lbm_resident_plan: %lld dependencies, room for %lld", (long long)pl.dep.size(), (long long)dep_cap);
+    *n_col_blocks = pl.n_col_blocks;
+    std::copy(pl.col_a.begin(), pl.col_a.end(), col_a);
+    std::copy(pl.dep_off.begin(), pl.dep_off.end(), dep_off);
+    if (dep) std::copy(pl.dep.begin(), pl.dep.end(), dep);
+    return LBM_OK;
+}
 
 int lbm_last_step_ms(lbm_t *h, float *ms)
 {
