@@ -235,7 +235,8 @@ def test_inlet_model_reproduces_the_apps_bit_for_bit():
         for it in (4, 5, 77, 500, 2222, 40000):
             app.set_inlets(lat, it)
             assert np.array_equal(m.row(it), lat.snapshot_walls()), (name, it)
-        assert np.array_equal(m.scales([4, 77, 2222]), np.array([m.scale(4), m.scale(77), m.scale(2222)]))
+        its = [4, 77, 2222, int(8.9 * m.sigma), int(9.0 * m.sigma), int(9.0 * m.sigma) + 1, int(40 * m.sigma)]
+        assert np.array_equal(m.scales(its), np.array([m.scale(it) for it in its]))
 
 
 def test_inlet_model_rejects_an_app_that_does_not_fit():
