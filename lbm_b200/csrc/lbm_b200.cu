@@ -291,6 +291,17 @@ static int ensure_err(lbm_handle *h)
     return LBM_OK;
 }
 
+// After a stream synchronisation: did a device-side wait give up?  Every call that hands results to the host checks this --
+// data that passed a timed-out wait is garbage and must not be returned as a result.
+static int wait_error(const lbm_handle *h)
+{
+    if (!h->h_err || !*(volatile unsigned int *)h->h_err) return LBM_OK;
+    const unsigned int e = *(volatile unsigned int *)h->h_err;
+    if (e & 0x80000000u)
+        return fail(LBM_E_STATE, "resident batch (stepr_kernel) timed out waiting for a neighbour block at update %u of the launch", e & 0x7fffffffu);
+    return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", e);
+}
+
 // Slab runs with peer halos: before a launch reads the halo columns (or stores into a neighbour's), both
 // neighbours must have published the sequence number of the last update group (lbm_peer_signal).
 static int peer_wait(lbm_handle *h)
@@ -1064,13 +1075,7 @@ int lbm_sync(lbm_t *h)
 {
     CHECK_H(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->h_err && *(volatile unsigned int *)h->h_err) {
-        const unsigned int e = *h->h_err;
-        if (e & 0x80000000u)
-            return fail(LBM_E_STATE, "resident batch (stepr_kernel) timed out waiting for a neighbour block at update %u of the launch", e & 0x7fffffffu);
-        return fail(LBM_E_STATE, "peer halo exchange timed out waiting for update group %u of a neighbour", e);
-    }
-    return LBM_OK;
+    return wait_error(h);
 }
 
 static int copy_field_h2d(lbm_handle *h, void *dev_cell0, int64_t dev_plane, const void *host, int nplanes)
@@ -1091,7 +1096,7 @@ static int copy_field_d2h(lbm_handle *h, const void *dev_cell0, int64_t dev_plan
                                    static_cast<const char *>(dev_cell0) + q * dev_plane * h->esz, h->lay.pitch * h->esz,
                                    w, (size_t)h->cfg.nxl, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return LBM_OK;
+    return wait_error(h);
 }
 
 static int upload_populations(lbm_t *h, const void *host, StateKind kind)
@@ -1657,7 +1662,7 @@ int lbm_set_tuning(lbm_t *h, const char *key, int64_t value)
         h->resident_blocks = (int)value;
         free_resident(h);
     } else if (!strcmp(key, "resident_timeout_ms")) {
-        if (value < 1) return fail(LBM_E_INVALID, "resident_timeout_ms must be positive");
+        if (value < 0) return fail(LBM_E_INVALID, "resident_timeout_ms must not be negative (0: a block gives up at its first unsuccessful poll -- tests of the error path)");
         h->resident_timeout_ms = value;
     } else if (!strcmp(key, "pdl")) {
         h->pdl = value != 0;
@@ -1723,6 +1728,7 @@ int lbm_get_forces(lbm_t *h, int64_t first, int64_t n, double *out)
     { int rc = reduce_dirty_forces(h); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(out, h->d_forces + first * nobs * 2, (size_t)n * nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    { int rc = wait_error(h); if (rc) return rc; }
     if (!h->force_const.empty())
         for (int64_t s = 0; s < n; s++) {
             if (first + s == 0 && h->force_skip0) continue;      // never produced by link blocks
@@ -1773,6 +1779,7 @@ int lbm_forces_now(lbm_t *h, double *out)
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)nobs * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(LBM_E_CUDA, "lbm_forces_now: %s", cudaGetErrorString(e));
+        if (!rc) rc = wait_error(h);
         if (!rc && !h->force_const.empty())
             for (int k = 0; k < 2 * nobs; k++) out[k] += h->force_const[k];
     }

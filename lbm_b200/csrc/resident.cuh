@@ -154,7 +154,7 @@ __device__ __forceinline__ bool resident_wait(const ResidentParams<T> &rp, const
             unsigned int v;
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
             if (v >= need) break;
-            if ((spins & 63u) == 0 && (clock64() - t0 > rp.timeout_clk || *(volatile unsigned int *)abort_w)) {
+            if (((spins & 63u) == 0 || rp.timeout_clk == 0) && (clock64() - t0 > rp.timeout_clk || *(volatile unsigned int *)abort_w)) {
                 ok = false;
                 break;
             }

@@ -167,3 +167,22 @@ def test_resident_batch_against_the_oracle():
     f, fo = np.array(cg.forces), np.array(co.forces)
     assert f.shape == fo.shape and np.max(np.abs(f - fo)) < 1e-9
     lg.close()
+
+
+def test_a_wait_that_gives_up_is_reported_not_hung():
+    """Time-out 0: a block gives up at its first unsuccessful poll of a neighbour's progress word.  The launch ends (every
+    block leaves at its next wait), and every call that would hand results to the host fails with the time-out error."""
+    from lbm_b200 import _capi as C
+    from lbm_b200.solver import Solver
+    s = Solver(200, 200, tau=0.58)
+    s.set_tuning("resident", 1)
+    s.set_tuning("resident_timeout_ms", 0)
+    s.set_walls(_rows(200, 200, 1, 5, False))
+    s.init_equilibrium(1.0)
+    s.step(1)
+    s.step(200, 0, 0)
+    with pytest.raises(C.LbmError, match="timed out"):
+        s.sync()
+    with pytest.raises(C.LbmError, match="timed out"):
+        s.populations("post_collision")
+    s.close()
