@@ -31,9 +31,10 @@
 // only where there are links.  A pause between two polls (__nanosleep) changes nothing.  A second form without flags and fences -- value and sequence number
 // in ONE store ("LL" entries) for the three populations that cross a block interface, link operands and corner inputs
 // through per-operand entries, rings of four versions -- was built, was bit-identical too and was SLOWER (4-12 us): the
-// per-entry polls and the extra L2 traffic of 16-byte entries cost more than the fences they replace.  Configs 3-4 move
-// 26-31 MB per update through L2 (~7 TB/s in either form): what is left for them is keeping the populations in shared
-// memory.
+// per-entry polls and the extra L2 traffic of 16-byte entries cost more than the fences they replace.  ncu on config 3:
+// L2 throughput 39 % of peak, 9.1 warps per issue at a barrier -- latency chains, not bandwidth; the link blocks (two
+// dependent phases, 4500-5300 cycles) set the pace.  What is left is fewer trips through L2 per update: populations that
+// stay in shared memory.
 //
 // Same per-cell functions as step_kernel (finish_cell_w; ibb_value restates link_block's expressions operation by
 // operation), hence bit-identical to single updates (tests/test_gpu_resident.py).  The per-link momentum-exchange
