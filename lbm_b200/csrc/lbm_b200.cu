@@ -1285,8 +1285,8 @@ int lbm_set_links(lbm_t *h, int32_t n_obstacles, const int64_t *offsets, const i
     }
     grp.push_back((int)cx.size());
     h->n_groups = (int)grp.size() - 1;
-    for (int g = 0; g < h->n_groups; g++) {        // (cells are sorted by column)
-        h->grp_x0.push_back(cx[grp[g]]);
+    for (int g = 0; g < h->n_groups && !cx.empty(); g++) {     // (cells are sorted by column; a slab that owns none of the
+        h->grp_x0.push_back(cx[grp[g]]);                         // links still has one -- empty -- group)
         h->grp_x1.push_back(cx[grp[g + 1] - 1]);
     }
     // immediate sums: one block (looping over the groups) while the per-link terms fit its shared memory, else one block

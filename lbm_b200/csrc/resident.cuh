@@ -87,11 +87,12 @@ __device__ __forceinline__ void resident_columns(const StepParams<T> &p, const T
     int x = x0, y = y0;
     while (x < x_end) {
         const int idx = x * p.pitch + y;
-        if (!(p.mask && p.mask[idx])) {
-            T G[9];
-            GlobalSource<T, true>{p, sshift}(x, y, G);
-            finish_cell_w<T, STRICT, kFused, true>(p, walls, scale, x, y, G, sshift, dshift);
-        }
+        // (the mask byte and the populations are loaded TOGETHER: the acquire fence of the wait has emptied L1, a mask load
+        // that decides whether to load at all would put a second L2 round trip in front of every pass)
+        const unsigned char m = p.mask ? p.mask[idx] : (unsigned char)0;
+        T G[9];
+        GlobalSource<T, true>{p, sshift}(x, y, G);
+        if (!m) finish_cell_w<T, STRICT, kFused, true>(p, walls, scale, x, y, G, sshift, dshift);
         y += kBlock;
         while (y >= p.ny) { y -= p.ny; x++; }
     }

@@ -186,3 +186,23 @@ def test_a_wait_that_gives_up_is_reported_not_hung():
     with pytest.raises(C.LbmError, match="timed out"):
         s.populations("post_collision")
     s.close()
+
+
+def test_slab_handle_whose_links_all_lie_elsewhere():
+    """A slab that owns none of the obstacle links (they belong to other slabs) still gets the link lists -- with one empty
+    group of boundary cells.  lbm_set_links must cope (the group's column range does not exist), the slab is updated like an
+    obstacle-free one, multi-update launches stay available and its force slots read zero."""
+    from lbm_b200.solver import Solver
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "run_turek30.npz"))
+    obs = [cases.Obstacle(z["boundary"], z["ibb"])]
+    assert int(z["boundary"][:, 0].max()) < 80
+    s = Solver(160, 30, tau=0.58, right_wall="pressure", x0=80, nxl=80)
+    s.set_links(obs)
+    assert s.can_stepn()
+    s.init_equilibrium(1.0, 0.02, 0.0)
+    s.set_walls(_rows(160, 30, 6, 5, True))
+    s.step(1)
+    s.step(5, 0, 1)
+    assert np.all(np.isfinite(s.populations("post_collision")))
+    assert np.array_equal(s.forces(0, 5), np.zeros((5, 1, 2)))
+    s.close()
