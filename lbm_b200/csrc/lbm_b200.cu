@@ -795,10 +795,7 @@ static int launch_band_group(lbm_handle *h, int src, int dst, int d, const int64
 }
 
 // ---------------------------------------------------------------------------------------
-// Resident batches (stepr_kernel, resident.cuh): block layout and dependency lists of the handle's lattice.
-// Column block i owns columns [i nx / n, (i+1) nx / n), reads one column beyond them; link group g owns the boundary
-// cells in columns [grp_x0, grp_x1] and reads two beyond (interpolated bounce-back).  i depends on j when the columns
-// one of them reads meet the columns the other writes.
+// Resident batches (stepr_kernel, resident.cuh): which lattices they are for, the block plan, the launch.
 static bool resident_candidate(const lbm_handle *h)
 {
     return (h->resident > 0 || (h->resident < 0 && h->n_cells > 0)) && h->temporal && !h->tb_force && !h->is_band && h->stream != nullptr && h->cfg.x0 == 0 && h->cfg.nxl == h->cfg.nx &&
@@ -1513,9 +1510,12 @@ int lbm_step(lbm_t *h, int64_t n_updates, int64_t first_row, int64_t row_stride,
     // population buffers keep their addresses; their contents are read when the graph runs).
     // (<= 2^19 cells: below the size at which multi-update kernels take over, so that a captured batch
     // consists of step_kernel launches only)
+    // (a batch that goes through stepr_kernel is one launch already -- and a cooperative launch cannot be captured)
+    const bool resident_takes_it = h->kind == kHaveF && resident_usable(h, n_updates - ((flags & LBM_STEP_MACRO_LAST) ? 1 : 0), 0, &rc);
+    if (rc) return rc;
     const bool graph_ok = h->use_graph && h->stream != nullptr && h->kind == kHaveF && n_updates >= 16 &&
                           h->cfg.nxl * h->cfg.ny <= (1LL << 19) && !h->peer[0].attached && !h->peer[1].attached &&
-                          !resident_candidate(h);   // (a resident batch is one launch already)
+                          !resident_takes_it;
     if (graph_ok) {
         lbm_handle::StepGraph *g = nullptr;
         for (auto &e : h->graphs)
