@@ -210,6 +210,33 @@ def test_batched_driver_equals_the_plain_loop(name, batch, pipeline):
         assert np.array_equal(getattr(la, k), getattr(lb, k)), k
 
 
+@pytest.mark.parametrize("j_stop", [5, 6, 7, 8, 13, 14, 15, 20, 21, 22])
+def test_pipelined_stop_on_every_position_of_a_batch(j_stop):
+    """A stop rule that fires on iteration j_stop, batches of 7 updates (iterations 1-7, 8-14, 15-21, ..): the stop on the
+    last iteration of a batch is seen one batch later (its drag/lift is slot 0 of the NEXT batch: the roll-back then re-runs
+    nothing), on the first iteration it discards a batch that was speculated in vain.  Same iteration count, force series
+    and final arrays as the plain loop."""
+    z = np.load(os.path.join(GOLDEN, "run_turek30.npz"))
+
+    class StopAt(cases.Turek):
+        def check_stop(self, it):
+            return it != j_stop
+
+    def mk():
+        return StopAt(L_lbm=30, Re_lbm=20.0, sigma=15, links=[cases.Obstacle(z["boundary"], z["ibb"])], stop="obs")
+    ca, cb = mk(), mk()
+    la, lb = LazyOracleLattice(ca), orc.OracleLattice(cb)
+    na = run(la, ca, batch=7, quiet=True)
+    nb = orc.run_loop(lb, cb)
+    assert na == nb == j_stop + 1
+    assert getattr(la, "rollbacks", 0) == 1 and la.max_in_flight == 2
+    assert np.array_equal(np.array(ca.forces), np.array(cb.forces))
+    if la._state == "streamed" and not la._advanced:
+        la._advance()
+    for k in ("g", "g_up", "rho", "u"):
+        assert np.array_equal(getattr(la, k), getattr(lb, k)), k
+
+
 def test_inlet_model_reproduces_the_apps_bit_for_bit():
     """InletModel (run.py): closed form of app.set_inlets for the restated cases and -- where the reference is
     checked out -- for the reference's own cavity / turek / poiseuille / array apps: every wall row it predicts
