@@ -22,7 +22,9 @@ callbacks -- while the device executes the next batch.  The drag/lift of a batch
 following batch (the sums of iteration i are produced by update i+1), so that iteration's observables / check_stop are
 replayed with the next batch.  A whole run then costs max(device, host) per iteration instead of their sum.  The
 speculation is given up where the app needs the fields (output iterations), at it_max, and when an 'obs' stop fires:
-the populations are rolled back to the start of the batch the stop lies in, exactly as without pipelining.  The app sees
+the populations are rolled back to the start of the batch the stop lies in (the starting states of three batches are
+kept: the one replayed, the one before it -- a stop on ITS last iteration is only seen now -- and the one speculated
+after it), exactly as without pipelining.  The app sees
 the same calls with the same values; only set_inlets / set_bc of a batch's last iteration come before the replay of
 that batch's earlier iterations.
 
@@ -133,7 +135,7 @@ def _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_ti
         if not np.array_equal(lattice._row, model.row(it - 1)):
             raise RuntimeError("inlet model no longer matches app.set_inlets at iteration %d" % (it - 1))
         scales = model.scales(np.arange(it - 1, it - 1 + n))
-        slot = serial[0] & 1
+        slot = serial[0] % 3                                  # (this batch, the one before, the one speculated after)
         serial[0] += 1
         if exact_stop:
             lattice.save_state(slot)
@@ -151,7 +153,7 @@ def _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_ti
             lattice._replay = None
         return app.check_stop(j)
 
-    cur = enqueue(1, False)
+    cur, prev = enqueue(1, False), None
     while True:
         it, n, last = cur["it"], cur["n"], cur["last"]
         chain = not (freq > 0 and last % freq == 0) and not (it_max is not None and last >= it_max)
@@ -173,19 +175,23 @@ def _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_ti
             if nxt is not None:
                 lattice.batch_result(nxt["token"])            # (speculated in vain)
             m = stopped_at - it + 1
-            lattice.restore_state(cur["slot"])
-            lattice._state = "streamed"
             if m > 0:
+                lattice.restore_state(cur["slot"])
+                lattice._state = "streamed"
                 lattice.batch_updates_ramp(model.base, cur["scales"][:m])
             else:
-                lattice._state = "macro_done"                 # (the iteration before the batch: its update is the saved state)
+                # the last iteration of the batch BEFORE this one (its drag/lift came with this batch): that batch once
+                # more from its own start, so that rho / u of its last update are the stored fields again
+                lattice.restore_state(prev["slot"])
+                lattice._state = "streamed"
+                lattice.batch_updates_ramp(model.base, prev["scales"])
             lattice.collision_stream()
             app.set_inlets(lattice, stopped_at)
             app.set_bc(lattice)
             it = stopped_at + 1
             break
         if chain:
-            cur = nxt
+            cur, prev = nxt, cur
             continue
         if not quiet:
             app.printings(last)
@@ -193,7 +199,7 @@ def _run_pipelined(lattice, app, model, batch, quiet, freq, stop_on_it, start_ti
         if not _tail_of_iteration(lattice, app, last):
             it = last + 1
             break
-        cur = enqueue(last + 1, False)
+        cur, prev = enqueue(last + 1, False), None
 
     if not quiet:
         print("# Loop time = {:f}".format(time.time() - start_time))

@@ -120,6 +120,7 @@ class LazyOracleLattice(orc.OracleLattice):
                 f = self._advance()
             forces.append(f)
             orc.OracleLattice.macro(self)
+            self.fields_stale = False
             self._state = "macro_done"
             if k + 1 < len(rows):
                 self._state = "streamed"             # same BC set for the following update
@@ -153,10 +154,14 @@ class LazyOracleLattice(orc.OracleLattice):
         self.__dict__.setdefault("_saved", {})[slot] = tuple(a.copy() for a in (self.g, self.g_up, self.rho, self.u)) + (self._advanced,)
 
     def restore_state(self, slot=0):
+        """(The real lattice restores the populations only: rho / u on the device stay those of the last update that was
+        EXECUTED.  Here they are inputs of the next update and have to come back, so staleness is tracked by a flag that
+        the next executed update clears: a run must not end with it set.)"""
         self.rollbacks = getattr(self, "rollbacks", 0) + 1
         for a, b in zip((self.g, self.g_up, self.rho, self.u), self._saved[slot][:4]):
             a[:] = b
         self._advanced = self._saved[slot][4]
+        self.fields_stale = True
 
 
 for _name in _BC:
@@ -230,6 +235,7 @@ def test_pipelined_stop_on_every_position_of_a_batch(j_stop):
     nb = orc.run_loop(lb, cb)
     assert na == nb == j_stop + 1
     assert getattr(la, "rollbacks", 0) == 1 and la.max_in_flight == 2
+    assert not la.fields_stale                  # rho / u belong to the iteration the run stopped on
     assert np.array_equal(np.array(ca.forces), np.array(cb.forces))
     if la._state == "streamed" and not la._advanced:
         la._advance()
